@@ -1,0 +1,288 @@
+// Stage (e): quarter-pixel adjust, person score and missing-joint refine
+// (/root/reference/src/keypoints/grouping.py:172-191, :276, :193-250, loop :278-282).
+//
+// The reference's refine makes, for every person, 17 passes over the full-resolution heatmap
+// and tag maps (80-96 % of its decode time).  Only joints a person is MISSING can change
+// (grouping.py:248), and for such a (person, joint) pair the answer is
+//     argmax_pix ( hm[k][pix] - rint(|tags[k][pix] - T_person|) ),  first index on ties,
+// where the subtracted term is a non-negative integer, so  value(pix) <= hm[k][pix].
+// That bound makes the search sparse:
+//   1. adjust_prepare_kernel (one warp per person) adjusts the detected joints, computes the
+//      person score and the person's mean tag T, lists the (person, joint) pairs to refine and
+//      seeds each pair's running best with the joint's top-k candidates;
+//   2. refine_scan_kernel walks the per-word maxima of the raw heatmap (written by the
+//      aggregation kernel, 1/32 of a map) and expands only words whose maximum can still beat
+//      or tie a pair's running best; bests are 64-bit keys (ordered value, ~index) merged with
+//      atomicMax, which implements "largest value, then lowest index" exactly;
+//   3. refine_apply_kernel turns the winning pixel into the refined joint.
+// All float arithmetic is the reference's float32 sequence (separate mul/add, IEEE sqrt, rint).
+#include "common.cuh"
+
+namespace hpd {
+
+namespace {
+
+struct RefineWs {
+  unsigned long long* keys;  // [B*K][M]   running best per listed (person, joint)
+  float* T;                  // [B][M][2]  mean tag per person
+  int32_t* miss_cnt;         // [B*K]
+  int32_t* miss_pid;         // [B*K][M]
+};
+
+__host__ __device__ inline size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+RefineWs carve(void* ws, int B, int K, int M) {
+  RefineWs r;
+  char* p = (char*)ws;
+  r.keys = (unsigned long long*)p;
+  p += align_up((size_t)B * K * M * 8, 256);
+  r.T = (float*)p;
+  p += align_up((size_t)B * M * 2 * 4, 256);
+  r.miss_cnt = (int32_t*)p;
+  p += align_up((size_t)B * K * 4, 256);
+  r.miss_pid = (int32_t*)p;
+  return r;
+}
+
+__device__ __forceinline__ unsigned ordered_u32(float v) {
+  const unsigned u = __float_as_uint(v);
+  return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+__device__ __forceinline__ float unordered_f32(unsigned o) {
+  return __uint_as_float((o & 0x80000000u) ? (o & 0x7fffffffu) : ~o);
+}
+__device__ __forceinline__ unsigned long long pack_key(float v, int idx) {
+  return ((unsigned long long)ordered_u32(v) << 32) | (unsigned)(~(unsigned)idx);
+}
+
+// hm - rint(||tag - T||) with the reference's float32 op sequence (grouping.py:221-222);
+// "+ 0.0f" folds -0 into +0 so that the ordered-bits compare agrees with np.argmax's ==.
+__device__ __forceinline__ float refine_value(float hm, float t0, float t1, float T0, float T1, int E) {
+  const float a = __fsub_rn(t0, T0);
+  float s = __fmul_rn(a, a);
+  if (E > 1) {
+    const float b = __fsub_rn(t1, T1);
+    s = __fadd_rn(s, __fmul_rn(b, b));
+  }
+  const float d = __fsqrt_rn(s);
+  return __fadd_rn(__fsub_rn(hm, rintf(d)), 0.0f);
+}
+
+__device__ __forceinline__ void quarter_offset(const float* __restrict__ m, int H, int W, int xi, int yi, float& x,
+                                               float& y) {
+  x += (m[(size_t)yi * W + min(xi + 1, W - 1)] > m[(size_t)yi * W + max(xi - 1, 0)]) ? 0.25f : -0.25f;
+  y += (m[(size_t)min(yi + 1, H - 1) * W + xi] > m[(size_t)max(yi - 1, 0) * W + xi]) ? 0.25f : -0.25f;
+}
+
+// one warp per person, one block per image
+__global__ void adjust_prepare_kernel(const float* __restrict__ agg_hm, const float* __restrict__ agg_tags,
+                                      const int32_t* __restrict__ idx_k, const int32_t* __restrict__ n_person, int K,
+                                      int M, int E, int H, int W, int do_adjust, int do_refine,
+                                      float* __restrict__ poses, float* __restrict__ person_scores, RefineWs ws) {
+  __shared__ float s_score[HPD_MAX_PEOPLE][HPD_MAX_KPTS];
+  __shared__ float s_tl[HPD_MAX_PEOPLE][HPD_MAX_KPTS][HPD_MAX_EMB];
+  __shared__ int s_cnt[HPD_MAX_KPTS];
+  const int b = blockIdx.x;
+  const int p = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int D = 3 + E;
+  const int P = n_person[b];
+  if (threadIdx.x < HPD_MAX_KPTS) s_cnt[threadIdx.x] = 0;
+  __syncthreads();
+  const float* hm_b = agg_hm + (size_t)b * K * H * W;
+  const float* tg_b = agg_tags + (size_t)b * K * H * W * E;
+  float T0 = 0.f, T1 = 0.f;
+  bool missing = false;
+  if (p < P) {
+    float score = 0.f, x = 0.f, y = 0.f;
+    float* d = poses + (((size_t)b * M + p) * K + lane) * D;
+    if (lane < K) {
+      x = d[0]; y = d[1]; score = d[2];
+      if (do_adjust && score != 0.f) {   // grouping.py:172-191
+        const int xi = (int)x, yi = (int)y;
+        quarter_offset(hm_b + (size_t)lane * H * W, H, W, xi, yi, x, y);
+        x += 0.5f; y += 0.5f;
+        d[0] = x; d[1] = y;
+      }
+      s_score[p][lane] = score;
+    }
+    // tags of the detected joints at the (truncated) adjusted coordinates (grouping.py:206-210)
+    const bool has = lane < K && score > 0.f;
+    const unsigned hmask = __ballot_sync(kFull, has);
+    if (has && do_refine) {
+      const int pos = __popc(hmask & ((1u << lane) - 1u));
+      const int xi = (int)x, yi = (int)y;
+      const float* t = tg_b + (((size_t)lane * H + yi) * W + xi) * E;
+      s_tl[p][pos][0] = t[0];
+      s_tl[p][pos][1] = (E > 1) ? t[1] : 0.f;
+    }
+    __syncwarp();
+    if (lane == 0) {
+      person_scores[(size_t)b * M + p] =
+          __fdiv_rn(__fadd_rn(0.0f, np_sum_pairwise8(&s_score[p][0], K, 1)), (float)K);   // grouping.py:276
+      if (do_refine) {
+        const int n = __popc(hmask);
+        float mv[HPD_MAX_EMB] = {0.f, 0.f};
+        if (n > 0) np_mean_vectors(&s_tl[p][0][0], n, E, HPD_MAX_EMB, mv);
+        else mv[0] = mv[1] = __int_as_float(0x7fc00000);
+        T0 = mv[0]; T1 = mv[1];
+        ws.T[((size_t)b * M + p) * 2 + 0] = T0;
+        ws.T[((size_t)b * M + p) * 2 + 1] = T1;
+      }
+    }
+    T0 = __shfl_sync(kFull, T0, 0);
+    T1 = __shfl_sync(kFull, T1, 0);
+    missing = do_refine && lane < K && score == 0.f;
+  } else if (p < M && lane == 0) {
+    person_scores[(size_t)b * M + p] = 0.f;
+  }
+  // list the pairs to refine and seed their running best with the joint's top-k candidates
+  if (missing) {
+    const int slot = atomicAdd(&s_cnt[lane], 1);
+    const size_t bk = (size_t)b * K + lane;
+    ws.miss_pid[bk * M + slot] = p;
+    const float* m = hm_b + (size_t)lane * H * W;
+    const float* t = tg_b + (size_t)lane * H * W * E;
+    unsigned long long best = 0ull;
+    for (int j = 0; j < M; ++j) {
+      const int idx = idx_k[bk * M + j];
+      const float v = refine_value(m[idx], t[(size_t)idx * E], (E > 1) ? t[(size_t)idx * E + 1] : 0.f, T0, T1, E);
+      const unsigned long long key = pack_key(v, idx);
+      best = key > best ? key : best;
+    }
+    ws.keys[bk * M + slot] = best;
+  }
+  __syncthreads();
+  if (threadIdx.x < K) ws.miss_cnt[(size_t)b * K + threadIdx.x] = do_refine ? s_cnt[threadIdx.x] : 0;
+}
+
+constexpr int kScanWarps = 4;
+constexpr int kScanWordsPerBlock = 1024;
+
+__global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const float* __restrict__ agg_hm,
+                                                                      const float* __restrict__ agg_tags,
+                                                                      const float* __restrict__ hmax, int K, int M,
+                                                                      int E, int H, int W, int wpr, RefineWs ws) {
+  const int bk = blockIdx.y;
+  const int cnt = ws.miss_cnt[bk];
+  if (cnt == 0) return;
+  const int b = bk / K;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nwords = H * wpr;
+  const int w_begin = blockIdx.x * kScanWordsPerBlock + warp * (kScanWordsPerBlock / kScanWarps);
+  const int w_end = min(w_begin + kScanWordsPerBlock / kScanWarps, nwords);
+  if (w_begin >= nwords) return;
+  const float* m = agg_hm + (size_t)bk * H * W;
+  const float* t = agg_tags + (size_t)bk * H * W * E;
+  const float* hx = hmax + (size_t)bk * nwords;
+
+  // lane q < cnt tracks listed pair q
+  float T0 = 0.f, T1 = 0.f;
+  unsigned long long best = ~0ull;
+  if (lane < cnt) {
+    const int p = ws.miss_pid[(size_t)bk * M + lane];
+    T0 = ws.T[((size_t)b * M + p) * 2 + 0];
+    T1 = ws.T[((size_t)b * M + p) * 2 + 1];
+    best = ws.keys[(size_t)bk * M + lane];
+  }
+  const unsigned long long best_in = best;
+  // a word matters if its raw maximum can reach the smallest running best among the pairs
+  unsigned thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
+
+  for (int base = w_begin; base < w_end; base += 32) {
+    const int wd = base + lane;
+    const float hv = wd < w_end ? hx[wd] : -INFINITY;
+    uint32_t pass = __ballot_sync(kFull, wd < w_end && ordered_u32(__fadd_rn(hv, 0.0f)) >= thr);
+    while (pass) {
+      const int l = __ffs(pass) - 1;
+      pass &= pass - 1;
+      const unsigned hw_o = ordered_u32(__fadd_rn(__shfl_sync(kFull, hv, l), 0.0f));
+      if (hw_o < thr) continue;
+      const int w2 = base + l;
+      const int y = w2 / wpr, x = (w2 % wpr) * 32 + lane;
+      const bool valid = x < W;
+      const int idx = y * W + x;
+      float pv = 0.f, t0 = 0.f, t1 = 0.f;
+      if (valid) {
+        pv = m[idx];
+        t0 = t[(size_t)idx * E];
+        if (E > 1) t1 = t[(size_t)idx * E + 1];
+      }
+      for (int q = 0; q < cnt; ++q) {
+        const unsigned long long bq = __shfl_sync(kFull, best, q);
+        if (hw_o < (unsigned)(bq >> 32)) continue;
+        const float v = refine_value(pv, t0, t1, __shfl_sync(kFull, T0, q), __shfl_sync(kFull, T1, q), E);
+        const unsigned long long key = valid ? pack_key(v, idx) : 0ull;
+        const unsigned hi = __reduce_max_sync(kFull, (unsigned)(key >> 32));
+        const unsigned lo = __reduce_max_sync(kFull, ((unsigned)(key >> 32) == hi) ? (unsigned)key : 0u);
+        const unsigned long long wbest = ((unsigned long long)hi << 32) | lo;
+        if (lane == q && wbest > best) best = wbest;
+      }
+      thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
+    }
+  }
+  if (lane < cnt && best > best_in) atomicMax(&ws.keys[(size_t)bk * M + lane], best);
+}
+
+__global__ void refine_apply_kernel(const float* __restrict__ agg_hm, int total, int K, int M, int E, int H, int W,
+                                    float* __restrict__ poses, RefineWs ws) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (bk, slot)
+  if (i >= total) return;
+  const int bk = i / M, slot = i % M;
+  if (slot >= ws.miss_cnt[bk]) return;
+  const int b = bk / K, k = bk % K;
+  const int p = ws.miss_pid[(size_t)bk * M + slot];
+  const unsigned long long key = ws.keys[(size_t)bk * M + slot];
+  const int idx = (int)(~(unsigned)key);
+  const float* m = agg_hm + (size_t)bk * H * W;
+  const float val = m[idx];
+  if (!(val > 0.f)) return;     // grouping.py:248 (the pair is listed only if its score == 0)
+  const int y = idx / W, x = idx % W;
+  float fx = (float)x + 0.5f, fy = (float)y + 0.5f;
+  quarter_offset(m, H, W, x, y, fx, fy);
+  float* d = poses + (((size_t)b * M + p) * K + k) * (3 + E);
+  d[0] = fx; d[1] = fy; d[2] = val;
+}
+
+}  // namespace
+
+size_t refine_workspace_bytes(const HpdParams* p) {
+  const size_t B = p->batch, K = p->num_kpts, M = p->max_people;
+  return align_up(B * K * M * 8, 256) + align_up(B * M * 2 * 4, 256) + align_up(B * K * 4, 256) +
+         align_up(B * K * M * 4, 256);
+}
+
+int launch_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* wsp, size_t ws_bytes, cudaStream_t st) {
+  if (!buf->agg_hm || !buf->agg_tags || !buf->hm_wmax || !buf->idx_k || !buf->poses || !buf->person_scores ||
+      !buf->n_person) {
+    set_error("hpd_adjust_refine: agg_hm, agg_tags, hm_wmax, idx_k, poses, person_scores, n_person are required");
+    return HPD_EINVAL;
+  }
+  if (!wsp || ws_bytes < refine_workspace_bytes(p)) {
+    set_error("hpd_adjust_refine: workspace of %zu bytes required, got %zu", refine_workspace_bytes(p), ws_bytes);
+    return HPD_EWORKSPACE;
+  }
+  if ((uintptr_t)wsp % 8 != 0) {
+    set_error("hpd_adjust_refine: workspace must be 8-byte aligned");
+    return HPD_EINVAL;
+  }
+  const int B = p->batch, K = p->num_kpts, M = p->max_people, E = p->emb, H = p->out_h, W = p->out_w;
+  const int wpr = (W + 31) / 32;
+  RefineWs ws = carve(wsp, B, K, M);
+  adjust_prepare_kernel<<<B, 32 * M, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->idx_k, buf->n_person, K, M, E, H, W,
+                                              p->do_adjust, p->do_refine, buf->poses, buf->person_scores, ws);
+  count_launch();
+  int rc = check_launch("adjust_prepare_kernel");
+  if (rc || !p->do_refine) return rc;
+  const int nwords = H * wpr;
+  const dim3 grid((nwords + kScanWordsPerBlock - 1) / kScanWordsPerBlock, B * K);
+  refine_scan_kernel<<<grid, kScanWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->hm_wmax, K, M, E, H, W, wpr,
+                                                       ws);
+  count_launch();
+  if ((rc = check_launch("refine_scan_kernel"))) return rc;
+  const int total = B * K * M;
+  refine_apply_kernel<<<(total + 255) / 256, 256, 0, st>>>(buf->agg_hm, total, K, M, E, H, W, buf->poses, ws);
+  count_launch();
+  return check_launch("refine_apply_kernel");
+}
+
+}  // namespace hpd

@@ -1,0 +1,106 @@
+"""Batched bottom-up decoder: the public entry a pipeline calls once per batch.
+
+``BottomUpDecoder.decode`` takes the raw HigherHRNet outputs of a batch (optionally of the flipped
+run and of several test scales) as CUDA tensors and enqueues the whole path -- fused aggregation +
+NMS, top-k, grouping, adjust, refine -- on the current stream through ``hpd_decode``.  Nothing is
+copied to the host until ``DecodeResult.to_numpy()`` is called, and then only the pose lists.
+
+The reference decodes one image per call (results.py:233-234 strips the batch dim); here the
+batch is a superset: image b of a batch gives exactly what the reference returns for that image.
+"""
+from typing import List, Optional, Sequence, Tuple
+
+import numpy as np
+import torch
+
+from . import ops
+
+
+class DecodeResult:
+    """Device-side result of one batch; ``to_numpy`` gives the reference's per-image return values."""
+
+    def __init__(self, bufs: ops.DecodeBuffers):
+        self.bufs = bufs
+        self.agg_hm = bufs.agg_hm          # [B,K,H,W]
+        self.agg_tags = bufs.agg_tags      # [B,K,H,W,E]
+        self.poses = bufs.poses            # [B,M,K,3+E]
+        self.person_scores = bufs.person_scores
+        self.n_person = bufs.n_person
+        self.flags = bufs.flags
+
+    def packed(self) -> torch.Tensor:
+        """One device tensor [B, M*K*(3+E) + M + 2] holding poses, person scores, count and flag,
+        so the device->host read of a batch is a single copy."""
+        B = self.poses.shape[0]
+        return torch.cat([self.poses.reshape(B, -1), self.person_scores,
+                          self.n_person.to(torch.float32)[:, None], self.flags.to(torch.float32)[:, None]], dim=1)
+
+    @staticmethod
+    def unpack(packed: np.ndarray, M: int, K: int, E: int) -> List[Tuple[np.ndarray, np.ndarray]]:
+        out = []
+        D = 3 + E
+        for row in packed:
+            P = int(row[-2])
+            fb = int(row[-1]) & 1
+            poses = row[: M * K * D].reshape(M, K, D)[:P].copy()
+            scores = row[M * K * D: M * K * D + M][:P].copy()
+            out.append(_finish(poses, scores, fb))
+        return out
+
+    def to_numpy(self) -> List[Tuple[np.ndarray, np.ndarray]]:
+        """[(grouped_joints [P,K,3+E], person_scores [P]) per image] -- MPPEHeatmapParser.parse's return."""
+        B, M, K, D = self.poses.shape
+        return self.unpack(self.packed().cpu().numpy(), M, K, D - 3)
+
+
+def _finish(poses: np.ndarray, scores: np.ndarray, fallback: int):
+    if fallback:
+        # grouping.py:262-269 builds this pseudo-person in float64 with score 0.01; the kernel wrote
+        # the float32 image of it.  Coordinates and tags are exact in both; restore the dtype/score.
+        poses = poses.astype(np.float64)
+        poses[..., 2] = 0.01
+        scores = poses[..., 2].mean(1)
+    return poses, scores
+
+
+class BottomUpDecoder:
+    def __init__(self, num_kpts: int = 17, max_num_people: int = 30, det_thr: float = 0.05, tag_thr: float = 0.5,
+                 device="cuda:0", adjust: bool = True, refine: bool = True):
+        if not torch.cuda.is_available():
+            raise ops._lib.HpdError("hpdecode needs a CUDA device (sm_100a); there is no CPU fallback")
+        ops._lib.lib()
+        self.num_kpts, self.max_num_people = num_kpts, max_num_people
+        self.det_thr, self.tag_thr = det_thr, tag_thr
+        self.adjust, self.refine = adjust, refine
+        self.device = torch.device(device)
+        self._bufs = {}
+
+    def buffers(self, B, H, W, E, slot=0) -> ops.DecodeBuffers:
+        key = (B, H, W, E, slot)
+        if key not in self._bufs:
+            self._bufs[key] = ops.DecodeBuffers(B, self.num_kpts, H, W, E, self.max_num_people, self.device)
+        return self._bufs[key]
+
+    def decode(self, scales: Sequence[dict], out_hw: Tuple[int, int], tag_scale: int = 0,
+               tags_preflipped: bool = False, slot: int = 0) -> DecodeResult:
+        """scales: one dict per test scale with CUDA float32 tensors hm_lo, hm_hi, tag [B,K,h,w] and,
+        for the flip test, hm_lo_f, hm_hi_f, tag_f (raw outputs of the flipped forward)."""
+        H, W = out_hw
+        B = scales[0]["hm_lo"].shape[0]
+        E = 2 if scales[tag_scale].get("tag_f") is not None else 1
+        bufs = self.buffers(B, H, W, E, slot)
+        params = ops.make_params(B, self.num_kpts, H, W, E, self.max_num_people, self.det_thr, self.tag_thr,
+                                 self.adjust, self.refine, len(scales), tag_scale, tags_preflipped=tags_preflipped)
+        ops.run_decode(scales, bufs, params)
+        return DecodeResult(bufs)
+
+    def decode_maps(self, agg_hm: torch.Tensor, agg_tags: torch.Tensor) -> DecodeResult:
+        """Aggregated maps [B,K,H,W], [B,K,H,W,E] -> poses (the MPPEHeatmapParser.parse entry)."""
+        B, K, H, W = agg_hm.shape
+        E = agg_tags.shape[4]
+        bufs = ops.DecodeBuffers(B, K, H, W, E, self.max_num_people, agg_hm.device, agg_hm.contiguous(),
+                                 agg_tags.contiguous())
+        params = ops.make_params(B, K, H, W, E, self.max_num_people, self.det_thr, self.tag_thr, self.adjust,
+                                 self.refine)
+        ops.run_decode(None, bufs, params)
+        return DecodeResult(bufs)

@@ -1,0 +1,76 @@
+"""-m gpu: the CUDA path (through the C ABI / torch.ops.hpd) against the CPU oracle, stage by stage.
+
+Bars (BASELINE.json north_star): NMS survivors, top-k indices and person/joint assignment bit-exact;
+float outputs within 1e-5 relative -- in practice every float below is compared BIT-exactly too,
+because the kernels replay the reference's float32/float64 operation order.
+"""
+import numpy as np
+import pytest
+import torch
+
+from hpdecode import synth
+
+pytestmark = pytest.mark.gpu
+
+RTOL = 1e-5   # the tolerance north_star states for float outputs
+
+
+def _dev(scales):
+    return [{k: torch.from_numpy(v).cuda() for k, v in s.items()} for s in scales]
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+CASES = [
+    # name, generator, kwargs, size, det_thr, tag_thr, M
+    ("netlike192_flip", synth.netlike, dict(batch=2, size=192, flip=True, seed=1), 192, 0.05, 0.5, 30),
+    ("netlike192_noflip", synth.netlike, dict(batch=1, size=192, flip=False, seed=2), 192, 0.05, 0.5, 30),
+    ("crowd192_flip", synth.crowd, dict(batch=2, size=192, persons=8, flip=True, seed=3), 192, 0.05, 0.5, 30),
+    ("crowd256_q", synth.crowd, dict(batch=1, size=256, persons=20, flip=True, seed=4, quantised=True), 256, 0.05, 0.5, 30),
+    ("crowd256_q_noflip", synth.crowd, dict(batch=1, size=256, persons=30, flip=False, seed=5, quantised=True), 256, 0.05, 0.5, 30),
+    ("crowd256_val", synth.crowd, dict(batch=1, size=256, persons=12, flip=False, seed=6), 256, 0.1, 1.0, 20),
+    ("netlike512_flip", synth.netlike, dict(batch=1, size=512, flip=True, seed=7), 512, 0.05, 0.5, 30),
+    ("crowd512_30", synth.crowd, dict(batch=2, size=512, persons=30, flip=True, seed=8), 512, 0.05, 0.5, 30),
+]
+
+
+@pytest.mark.parametrize("case", CASES, ids=[c[0] for c in CASES])
+def test_decode_matches_oracle(case, oracle):
+    from hpdecode import BottomUpDecoder
+    name, gen, kw, size, det, tthr, M = case
+    scales = gen(**kw)
+    B = kw["batch"]
+    dec = BottomUpDecoder(17, M, det, tthr, "cuda:0")
+    res = dec.decode(_dev(scales), (size, size))
+    torch.cuda.synchronize()
+    agg, tags = res.agg_hm.cpu().numpy(), res.agg_tags.cpu().numpy()
+    bufs = res.bufs
+    out = res.to_numpy()
+    for b in range(B):
+        hm_o, tg_o = oracle.aggregate(synth.image_slice(scales, b), (size, size))
+        assert np.array_equal(_bits(agg[b]), _bits(hm_o)), f"{name}[{b}] aggregated heatmaps"
+        assert np.array_equal(_bits(tags[b]), _bits(tg_o)), f"{name}[{b}] aggregated tags"
+        # NMS survivors (bit mask) and word maxima
+        nm, keep = oracle.nms(hm_o)
+        mask = bufs.nms_mask[b].cpu().numpy().view(np.uint32)
+        bits = ((mask[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(17, size, -1)[:, :, :size]
+        assert np.array_equal(bits.astype(np.uint8), keep), f"{name}[{b}] NMS survivors"
+        wm = bufs.nms_wmax[b].cpu().numpy()
+        assert np.array_equal(wm, nm.reshape(17, size, -1, 32).max(-1)), f"{name}[{b}] nms word max"
+        hx = bufs.hm_wmax[b].cpu().numpy()
+        assert np.array_equal(hx, hm_o.reshape(17, size, -1, 32).max(-1)), f"{name}[{b}] raw word max"
+        ref = oracle.parse(hm_o, tg_o, M, det, tthr)
+        assert np.array_equal(bufs.idx_k[b].cpu().numpy(), ref["idx_k"]), f"{name}[{b}] top-k indices"
+        assert np.array_equal(_bits(bufs.scores_k[b].cpu().numpy()), _bits(ref["scores_k"])), f"{name}[{b}] top-k scores"
+        assert np.array_equal(bufs.coords_k[b].cpu().numpy(), ref["coords_k"]), f"{name}[{b}] top-k coords"
+        assert np.array_equal(_bits(bufs.tags_k[b].cpu().numpy()), _bits(ref["tags_k"])), f"{name}[{b}] top-k tags"
+        gj, ps = out[b]
+        assert gj.shape == ref["grouped_joints"].shape, f"{name}[{b}] person count {gj.shape} vs {ref['grouped_joints'].shape}"
+        # assignment: which (person, joint) slots are filled and with which integer peak
+        assert np.array_equal(gj[..., 2] != 0, ref["grouped_joints"][..., 2] != 0), f"{name}[{b}] joint assignment"
+        np.testing.assert_allclose(gj, ref["grouped_joints"], rtol=RTOL, atol=0, err_msg=f"{name}[{b}] grouped joints")
+        np.testing.assert_allclose(ps, ref["person_scores"], rtol=RTOL, atol=0, err_msg=f"{name}[{b}] person scores")
+        assert np.array_equal(_bits(gj), _bits(ref["grouped_joints"])), f"{name}[{b}] grouped joints (bit-exact)"
+        assert np.array_equal(_bits(ps), _bits(ref["person_scores"])), f"{name}[{b}] person scores (bit-exact)"
