@@ -1,0 +1,83 @@
+"""CPU suite: libhpdecode.so loads, exports every symbol include/hpdecode.h declares, and the ctypes
+structs have the C layout (checked with a gcc-compiled probe).  No compute calls (no GPU here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "hpdecode.h")
+
+
+def _declared():
+    src = open(HEADER).read()
+    return re.findall(r"HPD_EXPORT\s+[\w\s\*]+?\b(hpd_\w+)\s*\(", src)
+
+
+def test_library_exports_every_declared_symbol():
+    from hpdecode import _lib
+    if not os.path.isfile(_lib.LIB_PATH):
+        import __graft_entry__
+        __graft_entry__.build()
+    names = _declared()
+    assert len(names) >= 11 and set(names) == set(_lib.EXPORTS)
+    L = ctypes.CDLL(_lib.LIB_PATH)
+    for n in names:
+        assert hasattr(L, n), n
+    assert _lib.lib().hpd_abi_version() == _lib.HPD_ABI_VERSION
+
+
+def test_ctypes_structs_match_c_layout(tmp_path):
+    from hpdecode import _lib
+    probe = tmp_path / "probe.c"
+    probe.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hpdecode.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                     "sizeof(HpdMap),sizeof(HpdScaleInputs),sizeof(HpdParams),sizeof(HpdBuffers),"
+                     "offsetof(HpdParams,det_thr),offsetof(HpdParams,joints_order));return 0;}\n")
+    exe = tmp_path / "probe"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)])
+    got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
+    want = [ctypes.sizeof(_lib.HpdMap), ctypes.sizeof(_lib.HpdScaleInputs), ctypes.sizeof(_lib.HpdParams),
+            ctypes.sizeof(_lib.HpdBuffers), _lib.HpdParams.det_thr.offset, _lib.HpdParams.joints_order.offset]
+    assert got == want
+
+
+def test_argument_validation_without_gpu():
+    """Validation happens before any launch, so the error path is testable on a CPU box."""
+    from hpdecode import _lib, ops
+    L = _lib.lib()
+    p = ops.make_params(1, 17, 16, 16, 1, 30, 0.05, 0.5)     # 256 px < 64*30: torch topk regime differs
+    b = _lib.HpdBuffers()
+    rc = L.hpd_topk(ctypes.byref(p), ctypes.byref(b), None)
+    assert rc == 1 and b"64*max_people" in L.hpd_last_error_string()
+    p = ops.make_params(1, 17, 256, 256, 3, 30, 0.05, 0.5)
+    assert L.hpd_group(ctypes.byref(p), ctypes.byref(b), None) == 1 and b"emb" in L.hpd_last_error_string()
+    p = ops.make_params(1, 17, 256, 256, 1, 40, 0.05, 0.5)
+    assert L.hpd_group(ctypes.byref(p), ctypes.byref(b), None) == 1 and b"max_people" in L.hpd_last_error_string()
+    p = ops.make_params(1, 17, 256, 256, 1, 30, 0.05, 0.5)
+    assert L.hpd_group(ctypes.byref(p), ctypes.byref(b), None) == 1 and b"required" in L.hpd_last_error_string()
+    n = ctypes.c_size_t(0)
+    assert L.hpd_workspace_bytes(ctypes.byref(p), ctypes.byref(n)) == 0 and n.value > 0
+
+
+def test_product_fails_loudly_without_cuda():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from hpdecode import BottomUpDecoder, MPPEHeatmapParser, _lib
+    with pytest.raises(_lib.HpdError):
+        BottomUpDecoder()
+    with pytest.raises(_lib.HpdError):
+        MPPEHeatmapParser(17)
+    with pytest.raises(_lib.HpdError):
+        torch.ops.hpd.nms(torch.zeros(1, 17, 64, 64))
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "pytorch-human-pose_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                src = open(os.path.join(dirpath, f)).read()
+                assert "cpu_oracle" not in src and "py_port" not in src and "hpd_oracle" not in src, f

@@ -1,0 +1,78 @@
+"""CPU suite: host-side logic -- synthetic generators, result packing, sharding and the
+world_size-2 gather over gloo (the N>1 path of bench.py without GPUs)."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from hpdecode import synth
+from hpdecode.decoder import DecodeResult, _finish
+from hpdecode.parallel import gather_packed, shard_range
+
+
+def test_synth_is_deterministic_and_shaped():
+    a = synth.netlike(2, 192, True, seed=3)
+    b = synth.netlike(2, 192, True, seed=3)
+    assert all(np.array_equal(a[0][k], b[0][k]) for k in a[0])
+    assert a[0]["hm_lo"].shape == (2, 17, 48, 48) and a[0]["hm_hi"].shape == (2, 17, 96, 96)
+    assert set(a[0]) == {"hm_lo", "hm_hi", "tag", "hm_lo_f", "hm_hi_f", "tag_f"}
+    c = synth.crowd(1, 256, persons=5, flip=False, seed=1)
+    assert set(c[0]) == {"hm_lo", "hm_hi", "tag"} and c[0]["hm_lo"].dtype == np.float32
+    ms = synth.netlike(1, 640, True, seed=1, scales=(0.5, 1.0, 1.5))
+    assert [s["hm_hi"].shape[-1] for s in ms] == [160, 320, 480]
+
+
+def test_unpack_and_fallback_dtype():
+    M, K, E = 4, 17, 2
+    D = 3 + E
+    row = np.zeros(M * K * D + M + 2, np.float32)
+    row[: 2 * K * D] = np.arange(2 * K * D)
+    row[M * K * D: M * K * D + 2] = [0.5, 0.25]
+    row[-2] = 2
+    poses, scores = DecodeResult.unpack(row[None], M, K, E)[0]
+    assert poses.shape == (2, K, D) and poses.dtype == np.float32 and list(scores) == [0.5, 0.25]
+    fb = np.zeros((1, K, D), np.float32)
+    fb[..., 2] = np.float32(0.01)
+    p, s = _finish(fb, np.zeros(1, np.float32), 1)
+    assert p.dtype == np.float64 and p[0, 0, 2] == 0.01 and s[0] == np.full((1, K), 0.01).mean(1)[0]
+
+
+def test_shard_range_partitions():
+    for n in (1, 7, 64, 65):
+        for w in (1, 2, 4, 8):
+            spans = [shard_range(n, r, w) for r in range(w)]
+            assert spans[0][0] == 0 and spans[-1][1] == n
+            assert all(spans[i][1] == spans[i + 1][0] for i in range(w - 1))
+            assert max(e - b for b, e in spans) - min(e - b for b, e in spans) <= 1
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    b, e = shard_range(5, rank, world)
+    packed = torch.arange(5 * 3, dtype=torch.float32).reshape(5, 3)[b:e].clone()
+    out = gather_packed(packed, dst=0)
+    if rank == 0:
+        q.put(out.numpy())
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_packed_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    assert np.array_equal(got, np.arange(15, dtype=np.float32).reshape(5, 3))
