@@ -1,0 +1,333 @@
+#!/usr/bin/env python
+"""Benchmark of the bottom-up decode path (BASELINE.json: decoded images/s, 512x512, HigherHRNet-W32, flip).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A step = one pass of the whole decode path (fused aggregation+NMS -> top-k -> grouping -> adjust/refine)
+over one batch of synthetic network outputs; at N > 1 every rank decodes its own batch (images shard
+naturally, weak scaling) and the packed pose lists are gathered on rank 0 with NCCL inside the step.
+Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every field.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "pytorch-human-pose_b200"))
+
+import numpy as np  # noqa: E402
+
+K_JOINTS, MAX_PEOPLE, DET_THR, TAG_THR = 17, 30, 0.05, 0.5
+METRIC = "decoded images/s (512x512, HigherHRNet-W32, flip)"
+
+
+def algorithmic_bytes_per_image(size: int, flip: bool) -> int:
+    """reads 4*K*f*(q^2+h^2) + 4*K*f*q^2, writes 4*K*S^2*(1+E)."""
+    f = 2 if flip else 1
+    q, h = size // 4, size // 2
+    return 4 * K_JOINTS * f * (q * q + h * h) + 4 * K_JOINTS * f * q * q + 4 * K_JOINTS * size * size * (1 + f)
+
+
+def make_inputs(batch: int, size: int, seed: int, unique: int = 8):
+    """`unique` distinct synthetic images tiled to the batch (generation is CPU-bound; addresses differ,
+    so tiling does not make the decode cheaper)."""
+    from hpdecode import synth
+    base = synth.netlike(min(unique, batch), size, flip=True, seed=seed)[0]
+    reps = -(-batch // min(unique, batch))
+    return {k: np.ascontiguousarray(np.concatenate([v] * reps)[:batch]) for k, v in base.items()}
+
+
+# ------------------------------------------------------------------------------------------------
+# CPU side: the reference arm / cpu_baseline (oracle/py_port.py = the reference's torch-CPU + NumPy calls)
+# ------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    import torch
+    torch.set_num_threads(1)
+    from oracle import py_port
+    img, size = args
+    gj, ps = py_port.decode_image([img], (size, size), MAX_PEOPLE, DET_THR, TAG_THR)
+    return gj.shape[0]
+
+
+class CpuPool:
+    """One process per host core, each decoding whole images with the Python port (how the reference runs:
+    one image per call, single-threaded NumPy/Python; the pool is the fair multi-core figure)."""
+
+    def __init__(self, size: int, cores: int, inputs):
+        import multiprocessing as mp
+        self.size, self.cores = size, cores
+        self.images = [{k: v[i] for k, v in inputs.items()} for i in range(inputs["hm_lo"].shape[0])]
+        self.pool = mp.get_context("spawn").Pool(cores)
+        self.pool.map(_cpu_worker, [(self.images[0], size)] * cores)     # import torch + warm caches, untimed
+
+    def step(self, n_images: int) -> float:
+        t = time.perf_counter()
+        self.pool.map(_cpu_worker, [(self.images[i % len(self.images)], self.size) for i in range(n_images)], chunksize=1)
+        return time.perf_counter() - t
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def host_cores() -> int:
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = min(host_cores(), 32)
+    inputs = make_inputs(min(8, args.batch), args.size, seed=1)
+    pool = CpuPool(args.size, cores, inputs)
+    sample = cores                                     # one image per core per step (~6 s of wall clock)
+    for _ in range(args.warmup):
+        pool.step(sample)
+    times = [pool.step(sample) for _ in range(args.steps)]
+    pool.close()
+    total = sum(times)
+    value = sample * args.steps / total
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
+                         "sample": f"{sample} images per step (one per core), oracle/py_port.py = the reference's "
+                                   "torch-CPU/NumPy/munkres calls; the reference itself is Python and cannot travel"},
+        "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"HigherHRNet-W32 {args.size}x{args.size}, batch {args.batch} per GPU, flip test, single scale "
+                        "(BASELINE configs[2], sharded by image)",
+            "batch_per_gpu": args.batch, "size": args.size, "flip": True, "max_people": MAX_PEOPLE,
+            "l2": "inputs (855 MB/batch) and outputs (3.4 GB/batch) exceed the 126 MB L2; no flush needed"}
+
+
+# ------------------------------------------------------------------------------------------------
+# GPU side
+# ------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index: int):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
+                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                      stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.f.read().splitlines():
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 6:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, parts[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        os.unlink(self.f.name)
+        if sm:
+            out = {"sm_mhz": statistics.median(sm), "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def measured_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.isfile(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from hpdecode import BottomUpDecoder, ops
+    from hpdecode.parallel import gather_packed_equal
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.gpus != world:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    B, S = args.batch, args.size
+    host = make_inputs(B, S, seed=1 + rank)
+    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+    resident = {k: v.to(dev) for k, v in pinned.items()}
+    staging = {k: torch.empty_like(v) for k, v in resident.items()}
+    dec = BottomUpDecoder(K_JOINTS, MAX_PEOPLE, DET_THR, TAG_THR, dev)
+    bufs = dec.buffers(B, S, S, 2)
+    params = ops.make_params(B, K_JOINTS, S, S, 2, MAX_PEOPLE, DET_THR, TAG_THR)
+    F = MAX_PEOPLE * K_JOINTS * 5 + MAX_PEOPLE + 2
+    gathered = torch.empty((world * B, F), device=dev) if (world > 1 and rank == 0) else None
+    result_host = torch.empty((B, F), dtype=torch.float32).pin_memory()
+    from hpdecode.decoder import DecodeResult
+
+    stages = ("aggregate_nms", "topk", "group", "adjust_refine")
+
+    def step(scales, events=None):
+        for i, st in enumerate(stages):
+            if events is not None:
+                events[i].record()
+            ops.run_stage(st, bufs, params, scales=scales)
+        if events is not None:
+            events[len(stages)].record()
+        packed = DecodeResult(bufs).packed()
+        if world > 1:
+            gather_packed_equal(packed, gathered, dst=0)
+        return packed
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- value: inputs resident in HBM -------------------------------------------------------------
+    for _ in range(max(args.warmup, 3)):
+        step([resident])
+    barrier()
+    evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(args.steps)]
+    sampler = ClockSampler(local) if rank == 0 else None
+    l0 = ops.launches_total()
+    t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    t0.record()
+    for i in range(args.steps):
+        step([resident], evs[i])
+    t1.record()
+    barrier()
+    launches = ops.launches_total() - l0
+    ms_total = t0.elapsed_time(t1)
+    stage_ms = [statistics.mean(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(args.steps)) for j in range(len(stages))]
+
+    # ---- e2e: host buffers, H2D of the inputs and D2H of the pose lists inside the timed region ---------
+    def e2e_step():
+        for k in staging:
+            staging[k].copy_(pinned[k], non_blocking=True)
+        packed = step([staging])
+        src = gathered if (world > 1 and rank == 0) else packed
+        result_host.copy_(src[:B], non_blocking=True)
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e2e_steps = max(3, min(args.steps, 10))
+    barrier()
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = e0.elapsed_time(e1)
+    clocks = sampler.stop() if sampler else None
+
+    # max over ranks
+    if world > 1:
+        t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_total, e2e_ms = t.tolist()
+
+    if rank == 0:
+        n_person = bufs.n_person.cpu().numpy()
+        peak, peak_src = measured_peak()
+        bytes_launch = B * algorithmic_bytes_per_image(S, True)
+        achieved = bytes_launch / (stage_ms[0] * 1e-3) / 1e9
+        traffic = None
+        tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
+        if os.path.isfile(tp):
+            try:
+                traffic = json.load(open(tp)).get("agg_nms_dram_bytes_per_launch")
+            except Exception:
+                traffic = None
+        line = {
+            "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded smooth random fields with default-init HigherHRNet value ranges; no dataset/checkpoint offline)",
+            "config": workload_config(args),
+            "roofline": {"bound": "hbm", "kernel": "agg_nms (fused aggregation + NMS)", "achieved": achieved, "peak": peak,
+                         "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": bytes_launch, "kernel_ms": stage_ms[0]},
+            "stage_ms": dict(zip(stages, stage_ms)),
+            "grouping": {"us_per_image": 1e3 * stage_ms[2] / B, "note": "one warp per image, latency-bound"},
+            "persons_per_image": float(n_person.mean()),
+            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in pinned.values())) * world,
+                    "d2h_bytes_per_step": int(B * F * 4), "steps": e2e_steps},
+            "gpu_launches": launches, "clocks": clocks,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            cores = min(host_cores(), 32)
+            pool = CpuPool(S, cores, {k: v[:8] for k, v in host.items()})
+            sample = cores * 2
+            sec = pool.step(sample)
+            pool.close()
+            line["cpu_baseline"] = {"value": sample / sec, "unit": "images/s", "cores": cores, "kind": "port",
+                                    "sample": f"{sample} images over {cores} processes in {sec:.1f} s (oracle/py_port.py)"}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -310,6 +310,12 @@ __global__ void __launch_bounds__(kAggThreads) agg_nms_generic_kernel(const AggA
   }
 }
 
+}  // namespace hpd
+namespace hpd {
+#include "aggregate_nms_x2.cuh"
+}  // namespace hpd
+namespace hpd {
+
 // ---------------------------------------------------------------------------------------------
 // standalone NMS (grouping.py:80-83) for callers that hand in aggregated maps
 // ---------------------------------------------------------------------------------------------
@@ -449,6 +455,29 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
   a.tags_preflipped = p->tags_preflipped;
   a.vec_ok = (a.W % 4 == 0) && ((uintptr_t)a.agg_hm % 16 == 0) && ((uintptr_t)a.agg_tags % 16 == 0);
 
+  // standard single-scale x2/x2/x4 layout -> specialised kernel (aggregate_nms_x2.cuh)
+  {
+    const ScaleDev& S = a.sc[0];
+    const bool fast = !p->force_generic && a.n_scales == 1 && S.hh == 2 * S.lh && S.hw == 2 * S.lw && a.H == 2 * S.hh &&
+                      a.W == 2 * S.hw && a.th == S.lh && a.tw == S.lw && a.W % 32 == 0 && S.lh >= 2 && S.lw >= 2 &&
+                      a.vec_ok;
+    if (fast) {
+      const int NW = a.W >= 512 ? 4 : (a.W >= 256 ? 2 : 1);
+      const size_t smem = sizeof(float) * x2::smem_floats(NW, a.E);
+      const dim3 grid((a.W + 128 * NW - 1) / (128 * NW), (a.H + x2::RB - 1) / x2::RB, a.B * a.K);
+#define HPD_X2_LAUNCH(E_, NW_)                                                                              \
+  do {                                                                                                      \
+    if (smem > 48 * 1024)                                                                                   \
+      cudaFuncSetAttribute(x2::agg_nms_x2_kernel<E_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    x2::agg_nms_x2_kernel<E_, NW_><<<grid, 32 * NW_, smem, st>>>(a);                                        \
+  } while (0)
+      if (a.E == 1) { if (NW == 4) HPD_X2_LAUNCH(1, 4); else if (NW == 2) HPD_X2_LAUNCH(1, 2); else HPD_X2_LAUNCH(1, 1); }
+      else          { if (NW == 4) HPD_X2_LAUNCH(2, 4); else if (NW == 2) HPD_X2_LAUNCH(2, 2); else HPD_X2_LAUNCH(2, 1); }
+#undef HPD_X2_LAUNCH
+      count_launch();
+      return check_launch("agg_nms_x2_kernel");
+    }
+  }
   const int lo_words = (a.LO_R * a.LO_C > a.E * a.TG_R * a.TG_C) ? a.LO_R * a.LO_C : a.E * a.TG_R * a.TG_C;
   const size_t smem = sizeof(float) * ((size_t)OT_R * OT_C + (size_t)OT_R * TW + (size_t)a.HI_R * a.HI_C + lo_words +
                                        4 * (OT_C + OT_R + a.HI_C + a.HI_R));

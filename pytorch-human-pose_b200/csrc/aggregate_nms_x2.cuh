@@ -1,0 +1,325 @@
+// Specialised fused aggregation + NMS kernel for the standard HigherHRNet single-scale layout:
+//   hm_lo, tag at 1/4 resolution, hm_hi at 1/2 resolution, output at full resolution
+//   (lo --x2--> hi, mean, --x2--> out ; tag --x4--> out).
+// Included by aggregate_nms.cu (needs AggArgs).  Bit-identical to the generic kernel: the taps and
+// weights below are what axis_tap() yields for exact x2 / x4 ratios (all weights are exact in f32),
+// including the clamped first/last rows and columns.
+//
+// Work decomposition (B200: issue-bound otherwise -- the generic kernel spends ~370 instructions
+// per output pixel; this one ~30, which leaves the kernel bound by HBM writes):
+//   * one CTA = a band of RB output rows x (128 * NW) columns of one (image, joint) plane;
+//   * phase 1 (all threads): flip-averaged quarter-res / half-res tiles and the tag tiles -> smem
+//     (coalesced loads, the flipped operand is read mirrored with the permuted joint index);
+//   * phase 2 (all threads): stage mean S at half resolution, in place, exact torch arithmetic;
+//   * phase 3 (per warp, no CTA barrier): every lane owns 4 adjacent output columns and walks
+//     down the rows with everything in registers: horizontal interpolation of each half-res row
+//     once (two 8-byte smem loads), vertical interpolation per row, one 16-byte store of the
+//     heatmap, 5-wide row maximum via warp shuffles (halo columns from a per-warp prologue),
+//     5-tall column maximum in a register window, survivor test, and per-32-pixel-word
+//     mask / maxima reduced over the 8 lanes of the word;
+//   * phase 4 (per warp): tags, same walking scheme with x4 taps, E-innermost 16-byte stores.
+#pragma once
+
+namespace x2 {
+
+constexpr int RB = 32;                 // output rows per CTA band (multiple of 4)
+constexpr int SR = RB / 2 + 4;         // half-res rows staged
+constexpr int LR = RB / 4 + 4;         // quarter-res rows staged (hm_lo)
+constexpr int TR = RB / 4 + 2;         // quarter-res rows staged (tags)
+constexpr int NROWS = RB + 4;          // output rows walked (band + 2 halo rows on each side)
+
+__host__ __device__ inline int SC(int NW) { return 64 * NW + 6; }   // half-res cols: hx0-3 ..
+__host__ __device__ inline int LC(int NW) { return 32 * NW + 4; }   // quarter-res cols: lx0-2 ..
+__host__ __device__ inline int TC(int NW) { return 32 * NW + 2; }   // quarter-res cols: lx0-1 ..
+__host__ __device__ inline size_t smem_floats(int NW, int E) {
+  return (size_t)SR * SC(NW) + (size_t)LR * LC(NW) + (size_t)E * TR * TC(NW) + (size_t)NW * NROWS * 4 + 4 * SR;
+}
+
+__device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
+
+__device__ __forceinline__ float max3(float a, float b, float c) { return fmaxf(fmaxf(a, b), c); }
+
+// x2 tap of output index o (input size I): generic axis_tap specialised, used in phase 2 only
+__device__ __forceinline__ void tap_x2(int o, int I, int& i0, int& i1, float& w0, float& w1) {
+  if (o == 0) { i0 = 0; i1 = (I > 1) ? 1 : 0; w0 = 1.f; w1 = 0.f; return; }
+  if (o & 1) { i0 = o >> 1; w0 = 0.75f; w1 = 0.25f; }
+  else       { i0 = (o >> 1) - 1; w0 = 0.25f; w1 = 0.75f; }
+  i1 = (i0 < I - 1) ? i0 + 1 : i0;
+}
+
+template <int E, int NW>
+__global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
+  extern __shared__ __align__(16) float smem[];
+  constexpr int sc = 64 * NW + 6, lc = 32 * NW + 4, tc = 32 * NW + 2;
+  float* sS = smem;                              // [SR][sc]   hi average, then stage mean S
+  float* sL = sS + SR * sc;                      // [LR][lc]   flip-averaged hm_lo
+  float* sT = sL + LR * lc;                      // [E][TR][tc] tags
+  float* sEdge = sT + E * TR * tc;               // [NW][NROWS][4] halo-column values per warp
+  int* sRowI0 = (int*)(sEdge + NW * NROWS * 4);  // [SR] phase-2 vertical taps (rows of sL)
+  int* sRowI1 = sRowI0 + SR;
+  float* sRowW0 = (float*)(sRowI1 + SR);
+  float* sRowW1 = sRowW0 + SR;
+
+  const ScaleDev& S = a.sc[0];
+  const int tid = threadIdx.x;
+  constexpr int nthr = 32 * NW;
+  const int warp = tid >> 5, lane = tid & 31;
+  const int bk = blockIdx.z, b = bk / a.K, k = bk % a.K, kf = a.flip[k];
+  const int H = a.H, W = a.W;
+  const int x0 = blockIdx.x * 128 * NW, y0 = blockIdx.y * RB;
+  const int hxo = x0 / 2 - 3, hyo = y0 / 2 - 2;     // origins of the half-res tile
+  const int lxo = x0 / 4 - 2, lyo = y0 / 4 - 2;     // origins of the quarter-res hm tile
+  const int txo = x0 / 4 - 1, tyo = y0 / 4 - 1;     // origins of the tag tiles
+
+  // ---------------- phase 1: stage inputs (clamped = replicated at the borders) ----------------
+  {
+    const float* p = S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc;
+    const float* pf = S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr;
+    for (int i = tid; i < LR * lc; i += nthr) {
+      const int r = i / lc, c = i - r * lc;
+      const int y = clampi(lyo + r, 0, S.lh - 1), x = clampi(lxo + c, 0, S.lw - 1);
+      float v = __ldg(p + (size_t)y * S.lw + x);
+      if (pf) v = __fmul_rn(__fadd_rn(v, __ldg(pf + (size_t)y * S.lw + (S.lw - 1 - x))), 0.5f);
+      sL[i] = v;
+    }
+  }
+  {
+    const float* p = S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc;
+    const float* pf = S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr;
+    for (int i = tid; i < SR * sc; i += nthr) {
+      const int r = i / sc, c = i - r * sc;
+      const int y = clampi(hyo + r, 0, S.hh - 1), x = clampi(hxo + c, 0, S.hw - 1);
+      float v = __ldg(p + (size_t)y * S.hw + x);
+      if (pf) v = __fmul_rn(__fadd_rn(v, __ldg(pf + (size_t)y * S.hw + (S.hw - 1 - x))), 0.5f);
+      sS[i] = v;
+    }
+  }
+#pragma unroll
+  for (int e = 0; e < E; ++e) {
+    const bool unflip = (e == 1) && !a.tags_preflipped;
+    const float* p = (e == 0) ? a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc
+                              : a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc;
+    for (int i = tid; i < TR * tc; i += nthr) {
+      const int r = i / tc, c = i - r * tc;
+      const int y = clampi(tyo + r, 0, a.th - 1), x = clampi(txo + c, 0, a.tw - 1);
+      sT[e * TR * tc + i] = __ldg(p + (size_t)y * a.tw + (unflip ? a.tw - 1 - x : x));
+    }
+  }
+  if (tid < SR) {   // vertical taps of phase 2: half-res row -> rows of sL
+    int i0, i1; float w0, w1;
+    tap_x2(clampi(hyo + tid, 0, S.hh - 1), S.lh, i0, i1, w0, w1);
+    sRowI0[tid] = i0 - lyo; sRowI1[tid] = i1 - lyo; sRowW0[tid] = w0; sRowW1[tid] = w1;
+  }
+  __syncthreads();
+
+  // ---------------- phase 2: S = (up2(lo) + hi) * 0.5 in place (results.py:225-226) -------------
+  for (int c = tid; c < sc; c += nthr) {
+    int c0, c1; float wx0, wx1;
+    tap_x2(clampi(hxo + c, 0, S.hw - 1), S.lw, c0, c1, wx0, wx1);
+    c0 -= lxo; c1 -= lxo;
+#pragma unroll 4
+    for (int r = 0; r < SR; ++r) {
+      const float* r0 = sL + sRowI0[r] * lc;
+      const float* r1 = sL + sRowI1[r] * lc;
+      const float up = lerp2(wx0, wx1, sRowW0[r], sRowW1[r], r0[c0], r0[c1], r1[c0], r1[c1]);
+      sS[r * sc + c] = __fmul_rn(__fadd_rn(up, sS[r * sc + c]), 0.5f);
+    }
+  }
+  __syncthreads();
+
+  // ---------------- phase 3a: per-warp prologue, values of the 4 halo columns ------------------
+  const int xw = x0 + 128 * warp;                 // first column of this warp's strip
+  const int ys = y0 - 2;                          // first walked row (even)
+  float* edge = sEdge + warp * NROWS * 4;
+  if (lane < 4) {
+    const int xe = (lane < 2) ? xw - 2 + lane : xw + 126 + lane;   // xw-2, xw-1, xw+128, xw+129
+    const bool in_img = xe >= 0 && xe < W;
+    // xe >= 126 whenever it is inside the image, so no first-column special case here
+    const int h = xe >> 1;
+    const int ca = ((xe & 1) ? h : h - 1) - hxo, cb = ca + 1;
+    const float wa = (xe & 1) ? 0.75f : 0.25f, wb = (xe & 1) ? 0.25f : 0.75f;
+    float hA = 0.f, hB = 0.f, hC;
+    if (in_img) {
+      hA = fmaf(wa, sS[0 * sc + ca], __fmul_rn(wb, sS[0 * sc + cb]));
+      hB = fmaf(wa, sS[1 * sc + ca], __fmul_rn(wb, sS[1 * sc + cb]));
+    }
+    for (int p = 0; p < NROWS / 2; ++p) {
+      const int ye = ys + 2 * p;
+      float ve = -INFINITY, vo = -INFINITY;
+      if (in_img) {
+        hC = fmaf(wa, sS[(p + 2) * sc + ca], __fmul_rn(wb, sS[(p + 2) * sc + cb]));
+        if (ye >= 0 && ye < H) ve = (ye == 0) ? fmaf(1.f, hB, __fmul_rn(0.f, hC)) : fmaf(0.25f, hA, __fmul_rn(0.75f, hB));
+        if (ye + 1 >= 0 && ye + 1 < H) vo = fmaf(0.75f, hB, __fmul_rn(0.25f, hC));
+        hA = hB; hB = hC;
+      }
+      edge[(2 * p) * 4 + lane] = ve;
+      edge[(2 * p + 1) * 4 + lane] = vo;
+    }
+  }
+  __syncwarp();
+
+  // ---------------- phase 3b: walk the rows, 4 columns per lane ------------------------------------
+  const int X0 = xw + 4 * lane;
+  const bool active = X0 < W;
+  {
+    const int sbase = 64 * warp + 2 * lane + 2;   // index of S[h0-1] in a tile row (even -> 8B aligned)
+    const bool x_first = (X0 == 0);
+    const float wa0 = x_first ? 1.f : 0.25f, wb0 = x_first ? 0.f : 0.75f;
+    auto hpass = [&](int r, float (&h)[4]) {
+      const float2 p = *reinterpret_cast<const float2*>(sS + r * sc + sbase);
+      const float2 q = *reinterpret_cast<const float2*>(sS + r * sc + sbase + 2);
+      const float a0 = x_first ? p.y : p.x, b0 = x_first ? q.x : p.y;
+      h[0] = fmaf(wa0, a0, __fmul_rn(wb0, b0));
+      h[1] = fmaf(0.75f, p.y, __fmul_rn(0.25f, q.x));
+      h[2] = fmaf(0.25f, p.y, __fmul_rn(0.75f, q.x));
+      h[3] = fmaf(0.75f, q.x, __fmul_rn(0.25f, q.y));
+    };
+    float hA[4], hB[4], hC[4];
+    hpass(0, hA);
+    hpass(1, hB);
+    // register windows: rm = row maxima of rows y-4..y-1 (r0 oldest), vq = values of rows y-2, y-1
+    float r0[4], r1[4], r2[4], r3[4], vq0[4], vq1[4];
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { r0[c] = r1[c] = r2[c] = r3[c] = -INFINITY; vq0[c] = vq1[c] = -INFINITY; }
+    float* hm_plane = a.agg_hm + ((size_t)b * a.K + k) * H * W;
+    const size_t wplane = ((size_t)b * a.K + k) * H * a.wpr;
+
+    auto process_row = [&](int y, int slot, const float (&v)[4]) {
+      // v: values of row y (-inf if the row or the columns are outside the image)
+      if (active && y >= y0 && y < y0 + RB && y < H)
+        *reinterpret_cast<float4*>(hm_plane + (size_t)y * W + X0) = make_float4(v[0], v[1], v[2], v[3]);
+      // 5-wide row maximum: own 4 + 2 from each neighbour lane (halo columns for lanes 0 / 31)
+      float l2 = __shfl_up_sync(kFull, v[2], 1), l3 = __shfl_up_sync(kFull, v[3], 1);
+      float q0 = __shfl_down_sync(kFull, v[0], 1), q1 = __shfl_down_sync(kFull, v[1], 1);
+      if (lane == 0) { l2 = edge[slot * 4 + 0]; l3 = edge[slot * 4 + 1]; }
+      if (lane == 31) { q0 = edge[slot * 4 + 2]; q1 = edge[slot * 4 + 3]; }
+      const float pb = fmaxf(v[0], v[1]), pc = fmaxf(v[2], v[3]);
+      float rm[4];
+      rm[0] = max3(fmaxf(l2, l3), pb, v[2]);
+      rm[1] = max3(l3, pb, pc);
+      rm[2] = max3(pb, pc, q0);
+      rm[3] = max3(v[1], pc, fmaxf(q0, q1));
+      // centre row yc = y - 2: 5-tall column maximum over rows y-4..y
+      const int yc = y - 2;
+      if (yc >= y0 && yc < y0 + RB && yc < H) {   // uniform over the CTA
+        float hm4 = -INFINITY, wm4 = -INFINITY;
+        unsigned nib = 0;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          const float m = max3(max3(r0[c], r1[c], r2[c]), r3[c], rm[c]);
+          const float vc = vq0[c];
+          const bool keep = active && (m == vc);
+          const float nv = keep ? vc : __fmul_rn(vc, 0.0f);
+          nib |= keep ? (1u << c) : 0u;
+          if (active) { hm4 = fmaxf(hm4, vc); wm4 = fmaxf(wm4, nv); }
+        }
+        unsigned bits = nib << (4 * (lane & 7));
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          bits |= __shfl_xor_sync(kFull, bits, o);
+          hm4 = fmaxf(hm4, __shfl_xor_sync(kFull, hm4, o));
+          wm4 = fmaxf(wm4, __shfl_xor_sync(kFull, wm4, o));
+        }
+        if ((lane & 7) == 0 && active) {
+          const size_t w = wplane + (size_t)yc * a.wpr + (X0 >> 5);
+          a.mask[w] = bits;
+          a.wmax[w] = wm4;
+          a.hmax[w] = hm4;
+        }
+      }
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        r0[c] = r1[c]; r1[c] = r2[c]; r2[c] = r3[c]; r3[c] = rm[c];
+        vq0[c] = vq1[c]; vq1[c] = v[c];
+      }
+    };
+
+#pragma unroll 1
+    for (int p = 0; p < NROWS / 2; ++p) {
+      const int ye = ys + 2 * p;
+      hpass(p + 2, hC);
+      float ve[4], vo[4];
+      const bool e_in = active && ye >= 0 && ye < H, o_in = active && ye + 1 >= 0 && ye + 1 < H;
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        const float t0 = (ye == 0) ? fmaf(1.f, hB[c], __fmul_rn(0.f, hC[c])) : fmaf(0.25f, hA[c], __fmul_rn(0.75f, hB[c]));
+        ve[c] = e_in ? t0 : -INFINITY;
+        vo[c] = o_in ? fmaf(0.75f, hB[c], __fmul_rn(0.25f, hC[c])) : -INFINITY;
+      }
+      process_row(ye, 2 * p, ve);
+      process_row(ye + 1, 2 * p + 1, vo);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { hA[c] = hB[c]; hB[c] = hC[c]; }
+    }
+  }
+
+  // ---------------- phase 4: tags, x4 taps (results.py:229-230) -------------------------------------
+  if (active) {
+    const int q = X0 >> 2;                       // this lane's quarter-res column
+    const int tb = q - 1 - txo;                  // index of T[q-1] in a tile row
+    const bool x_first = (q == 0);
+    // columns 4q+{0,1}: taps (q-1,q) weights (.375,.625),(.125,.875); 4q+{2,3}: (q,q+1) (.875,.125),(.625,.375)
+    const float wa0 = x_first ? 1.f : 0.375f, wb0 = x_first ? 0.f : 0.625f;
+    const float wa1 = x_first ? 1.f : 0.125f, wb1 = x_first ? 0.f : 0.875f;
+    float hA[E][4], hB[E][4];
+    auto hpass = [&](int r, float (&h)[E][4]) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float* t = sT + e * TR * tc + r * tc + tb;
+        const float t0 = t[0], t1 = t[1], t2 = t[2];
+        const float a0 = x_first ? t1 : t0, b0 = x_first ? t2 : t1;
+        h[e][0] = fmaf(wa0, a0, __fmul_rn(wb0, b0));
+        h[e][1] = fmaf(wa1, a0, __fmul_rn(wb1, b0));
+        h[e][2] = fmaf(0.875f, t1, __fmul_rn(0.125f, t2));
+        h[e][3] = fmaf(0.625f, t1, __fmul_rn(0.375f, t2));
+      }
+    };
+    float* tg_plane = a.agg_tags + ((size_t)b * a.K + k) * H * W * E;
+    auto emit = [&](int y, float wy0, float wy1, const float (&A)[E][4], const float (&Bv)[E][4]) {
+      if (y < y0 || y >= y0 + RB || y >= H) return;
+      float o[E][4];
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[e][c] = fmaf(wy0, A[e][c], __fmul_rn(wy1, Bv[e][c]));
+      float* dst = tg_plane + ((size_t)y * W + X0) * E;
+      if (E == 1) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[E - 1][0], o[0][1], o[E - 1][1]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[0][2], o[E - 1][2], o[0][3], o[E - 1][3]);
+      }
+    };
+    // tile rows: r <-> quarter-res row tyo + r = y0/4 - 1 + r.  Rows y0, y0+1 use (i-1, i) with
+    // i = y0/4, i.e. tile rows (0, 1); then each group of 4 rows 4i+2..4i+5 uses rows (i, i+1).
+    hpass(0, hA);
+    hpass(1, hB);
+    if (y0 == 0) {          // first two rows of the image: src clamps to 0 -> taps (row 0, row 1), weights (1, 0)
+      float hC[E][4];
+      hpass(2, hC);         // tile row 1 = image row 0, tile row 2 = image row 1
+      emit(0, 1.f, 0.f, hB, hC);
+      emit(1, 1.f, 0.f, hB, hC);
+    } else {
+      emit(y0, 0.375f, 0.625f, hA, hB);
+      emit(y0 + 1, 0.125f, 0.875f, hA, hB);
+    }
+#pragma unroll 1
+    for (int g = 0; g < RB / 4; ++g) {
+      // rows y0 + 4g + 2 .. y0 + 4g + 5 : taps (tile row g+1, tile row g+2)
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) hA[e][c] = hB[e][c];
+      hpass(g + 2, hB);
+      const int y = y0 + 4 * g + 2;
+      emit(y, 0.875f, 0.125f, hA, hB);
+      emit(y + 1, 0.625f, 0.375f, hA, hB);
+      if (g + 1 < RB / 4) {
+        emit(y + 2, 0.375f, 0.625f, hA, hB);
+        emit(y + 3, 0.125f, 0.875f, hA, hB);
+      }
+    }
+  }
+}
+
+}  // namespace x2

@@ -1,0 +1,168 @@
+"""-m gpu: stage-level checks -- specialised vs generic aggregation kernel, strided inputs,
+multi-scale aggregation, and the reference's public methods one by one through the drop-in classes."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from hpdecode import synth
+
+pytestmark = pytest.mark.gpu
+
+
+def _dev(scales):
+    return [{k: torch.from_numpy(v).cuda() for k, v in s.items()} for s in scales]
+
+
+def _bits(a):
+    return np.ascontiguousarray(a, np.float32).view(np.uint32)
+
+
+def _run_aggregate(scales, H, W, E, force_generic, tags_preflipped=False, tag_scale=0):
+    from hpdecode import ops
+    B = scales[0]["hm_lo"].shape[0]
+    bufs = ops.DecodeBuffers(B, 17, H, W, E, 30, "cuda:0")
+    for t in (bufs.agg_hm, bufs.agg_tags, bufs.nms_wmax, bufs.hm_wmax):
+        t.fill_(float("nan"))
+    bufs.nms_mask.fill_(-1)
+    p = ops.make_params(B, 17, H, W, E, 30, 0.05, 0.5, num_scales=len(scales), tag_scale=tag_scale,
+                        tags_preflipped=tags_preflipped)
+    p.force_generic = int(force_generic)
+    ops.run_stage("aggregate_nms", bufs, p, scales=scales)
+    torch.cuda.synchronize()
+    return bufs
+
+
+def _rand_maps(B, lh, lw, flip, seed):
+    g = torch.Generator().manual_seed(seed)
+    d = {"hm_lo": torch.randn(B, 17, lh, lw, generator=g), "hm_hi": torch.randn(B, 17, 2 * lh, 2 * lw, generator=g),
+         "tag": torch.randn(B, 17, lh, lw, generator=g)}
+    if flip:
+        d.update(hm_lo_f=torch.randn(B, 17, lh, lw, generator=g), hm_hi_f=torch.randn(B, 17, 2 * lh, 2 * lw, generator=g),
+                 tag_f=torch.randn(B, 17, lh, lw, generator=g))
+    return {k: v.cuda() for k, v in d.items()}
+
+
+@pytest.mark.parametrize("lh,lw,flip,B", [(128, 128, True, 2), (128, 128, False, 1), (48, 48, True, 1), (40, 72, True, 1),
+                                           (160, 160, True, 1), (64, 176, False, 2), (32, 256, True, 1), (12, 12, True, 1)])
+def test_specialised_kernel_is_bit_identical_to_generic(lh, lw, flip, B):
+    """aggregate_nms_x2 vs the generic kernel on every output, incl. borders, partial warps (W % 128 != 0),
+    several CTAs per row (W > 512) and tiny maps."""
+    s = _rand_maps(B, lh, lw, flip, seed=lh * 1000 + lw)
+    H, W, E = 4 * lh, 4 * lw, 2 if flip else 1
+    fast = _run_aggregate([s], H, W, E, False)
+    slow = _run_aggregate([s], H, W, E, True)
+    for name in ("agg_hm", "agg_tags", "nms_mask", "nms_wmax", "hm_wmax"):
+        a, b = getattr(fast, name).cpu().numpy(), getattr(slow, name).cpu().numpy()
+        assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{name} differs ({lh}x{lw}, flip={flip})"
+
+
+def test_tags_preflipped_mode():
+    """from_preds' calling convention: second tag map already un-flipped / permuted (model.py:91-94)."""
+    s = _rand_maps(1, 64, 64, True, seed=9)
+    pre = dict(s)
+    pre["tag_f"] = torch.flip(s["tag_f"], [3])[:, synth.COCO_FLIP_INDEX].contiguous()
+    a = _run_aggregate([s], 256, 256, 2, False)
+    for force in (False, True):
+        b = _run_aggregate([pre], 256, 256, 2, force, tags_preflipped=True)
+        assert torch.equal(a.agg_tags, b.agg_tags)
+
+
+def test_strided_channel_slice_inputs():
+    """hm_lo / tag arrive as channel slices of one 34-channel tensor (higher_hrnet.py:78-79)."""
+    g = torch.Generator().manual_seed(3)
+    both = torch.randn(2, 34, 64, 64, generator=g).cuda()
+    hi = torch.randn(2, 17, 128, 128, generator=g).cuda()
+    s_view = {"hm_lo": both[:, :17], "tag": both[:, 17:], "hm_hi": hi}
+    s_copy = {k: v.contiguous() for k, v in s_view.items()}
+    a = _run_aggregate([s_view], 256, 256, 1, False)
+    b = _run_aggregate([s_copy], 256, 256, 1, False)
+    c = _run_aggregate([s_view], 256, 256, 1, True)
+    for name in ("agg_hm", "agg_tags", "nms_mask"):
+        assert torch.equal(getattr(a, name), getattr(b, name)) and torch.equal(getattr(a, name), getattr(c, name))
+
+
+def test_multiscale_aggregate_matches_oracle(oracle):
+    """BASELINE config 3 semantics (scales 0.5/1.0/1.5 + flip, tags from scale 1.0): generic kernel."""
+    scales = synth.netlike(1, 512, True, seed=41, scales=(0.5, 1.0, 1.5))
+    bufs = _run_aggregate(_dev(scales), 512, 512, 2, False, tag_scale=1)
+    hm_o, tg_o = oracle.aggregate(synth.image_slice(scales, 0), (512, 512), tag_scale=1)
+    assert np.array_equal(_bits(bufs.agg_hm[0].cpu().numpy()), _bits(hm_o))
+    assert np.array_equal(_bits(bufs.agg_tags[0].cpu().numpy()), _bits(tg_o))
+    nm, keep = oracle.nms(hm_o)
+    mask = bufs.nms_mask[0].cpu().numpy().view(np.uint32)
+    bits = ((mask[..., None] >> np.arange(32, dtype=np.uint32)) & 1).reshape(17, 512, -1)
+    assert np.array_equal(bits.astype(np.uint8), keep)
+
+
+def test_resize_op_matches_oracle(oracle):
+    g = torch.Generator().manual_seed(5)
+    for (ih, iw, oh, ow) in [(64, 64, 128, 128), (128, 96, 512, 384), (120, 120, 160, 160), (80, 80, 80, 80)]:
+        x = torch.randn(2, 5, ih, iw, generator=g)
+        got = torch.ops.hpd.resize_bilinear(x.cuda(), oh, ow).cpu().numpy()
+        assert np.array_equal(_bits(got), _bits(oracle.resize_bilinear(x.numpy(), oh, ow)))
+
+
+def test_parser_api_matches_oracle(oracle):
+    """The reference's public methods one by one: nms, top_k, match_by_tag, adjust, refine, parse."""
+    from hpdecode import MPPEHeatmapParser
+    scales = synth.crowd(1, 256, persons=14, flip=True, seed=51)
+    hm, tg = oracle.aggregate(synth.image_slice(scales, 0), (256, 256))
+    parser = MPPEHeatmapParser(17, 30, 0.05, 0.5)
+    thm, ttg = torch.from_numpy(hm), torch.from_numpy(tg)      # CPU tensors are accepted like in the reference
+    nm, _ = oracle.nms(hm)
+    assert np.array_equal(_bits(parser.nms(thm[None])[0].cpu().numpy()), _bits(nm))
+    tags_k, coords_k, scores_k = parser.top_k(thm, ttg)
+    ref = oracle.parse(hm, tg, 30, 0.05, 0.5)
+    assert np.array_equal(coords_k, ref["coords_k"]) and coords_k.dtype == np.int32
+    assert np.array_equal(_bits(tags_k), _bits(ref["tags_k"])) and np.array_equal(_bits(scores_k), _bits(ref["scores_k"]))
+    matched = parser.match_by_tag(tags_k, coords_k, scores_k)
+    want, _ = oracle.match_by_tag(ref["tags_k"], ref["coords_k"], ref["scores_k"], 0.05, 0.5)
+    assert np.array_equal(_bits(matched), _bits(want))
+    gj, ps = parser.parse(thm, ttg)
+    assert np.array_equal(_bits(gj), _bits(ref["grouped_joints"])) and np.array_equal(_bits(ps), _bits(ref["person_scores"]))
+    no_refine = oracle.parse(hm, tg, 30, 0.05, 0.5, refine=False)["grouped_joints"]
+    adj = parser.adjust(matched.copy(), hm)
+    assert np.array_equal(_bits(adj), _bits(no_refine))
+    person = adj[0].copy()
+    assert np.array_equal(_bits(parser.refine(hm, tg, person)), _bits(ref["grouped_joints"][0]))
+
+
+def test_from_preds_and_fallback_dtype(oracle):
+    """from_preds receives flip-averaged heatmaps and [tag, unflipped flip tag] like the reference; an empty
+    scene returns the float64 pseudo-person (grouping.py:262-269)."""
+    from hpdecode import InferenceKeypointsResult
+    from oracle import golden_cases
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "empty256_fallback.npz"))
+    scales, size, M, det, tthr = golden_cases.make_inputs("empty256_fallback")
+    s = {k: torch.from_numpy(v) for k, v in scales[0].items()}
+    FL = synth.COCO_FLIP_INDEX
+    hms = [(s["hm_lo"] + torch.flip(s["hm_lo_f"], [3])[:, FL]) / 2, (s["hm_hi"] + torch.flip(s["hm_hi_f"], [3])[:, FL]) / 2]
+    tags = [s["tag"], torch.flip(s["tag_f"], [3])[:, FL].contiguous()]
+    res = InferenceKeypointsResult.from_preds(None, None, torch.zeros(3, size, size), [h.cuda() for h in hms],
+                                              [t.cuda() for t in tags], [], (size, size), (size // 2, size // 2), det, tthr, M)
+    assert res.kpts_scores.dtype == np.float64 and res.obj_scores.dtype == np.float64
+    assert np.array_equal(res.kpts_scores, g["grouped_joints"][..., 2])
+    assert np.array_equal(res.kpts_tags, g["grouped_joints"][..., 3:])
+    assert np.array_equal(res.obj_scores, g["person_scores"])
+    assert golden_cases.sha(res.kpts_heatmaps) == str(g["agg_hm_sha"])
+
+
+@pytest.mark.parametrize("name", ["netlike192_flip", "crowd256_q_flip", "crowd256_val_m20", "empty256_fallback",
+                                  "crowd512_30_flip", "netlike512_flip"])
+def test_decode_matches_committed_reference_goldens(name):
+    """The CUDA path against tests/golden/*.npz -- outputs of the UNMODIFIED reference, no oracle in between."""
+    from hpdecode import BottomUpDecoder
+    from oracle import golden_cases
+    g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))
+    scales, size, M, det, tthr = golden_cases.make_inputs(name)
+    assert golden_cases.inputs_digest(scales) == str(g["inputs_digest"])
+    dec = BottomUpDecoder(17, M, det, tthr, "cuda:0")
+    res = dec.decode(_dev(scales), (size, size))
+    assert golden_cases.sha(res.agg_hm[0].cpu().numpy()) == str(g["agg_hm_sha"])
+    assert golden_cases.sha(res.agg_tags[0].cpu().numpy()) == str(g["agg_tags_sha"])
+    assert np.array_equal(res.bufs.idx_k[0].cpu().numpy(), g["idx_k"])
+    gj, ps = res.to_numpy()[0]
+    assert gj.dtype == g["grouped_joints"].dtype
+    assert np.array_equal(gj, g["grouped_joints"]) and np.array_equal(ps, g["person_scores"])
