@@ -86,7 +86,9 @@ __device__ __forceinline__ void nms_tile(const float* __restrict__ outT, float* 
       const float nv = keep ? v : __fmul_rn(v, 0.0f);
       const uint32_t bits = __ballot_sync(kFull, keep);
       const float ninf = -INFINITY;
-      const float wm = warp_max_float(inside ? nv : ninf);
+      // word maximum of the NMS'd values; a suppressed pixel contributes +0 (the sign of its x*0 is
+      // irrelevant to every comparison made on the word maximum)
+      const float wm = warp_max_float(inside ? (keep ? v : 0.0f) : ninf);
       const float hm = warp_max_float(inside ? v : ninf);
       if (lane == 0) {
         const size_t w = (size_t)y * wpr + (x0 >> 5) + half;

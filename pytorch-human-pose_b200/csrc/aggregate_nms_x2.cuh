@@ -32,7 +32,7 @@ __host__ __device__ inline int SC(int NW) { return 64 * NW + 6; }   // half-res 
 __host__ __device__ inline int LC(int NW) { return 32 * NW + 4; }   // quarter-res cols: lx0-2 ..
 __host__ __device__ inline int TC(int NW) { return 32 * NW + 2; }   // quarter-res cols: lx0-1 ..
 __host__ __device__ inline size_t smem_floats(int NW, int E) {
-  return (size_t)SR * SC(NW) + (size_t)LR * LC(NW) + (size_t)E * TR * TC(NW) + (size_t)NW * NROWS * 4 + 4 * SR;
+  return (size_t)SR * SC(NW) + (size_t)LR * LC(NW) + (size_t)E * TR * TC(NW) + (size_t)NW * NROWS * 4 + 4 * SR + 4;
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -47,6 +47,37 @@ __device__ __forceinline__ void tap_x2(int o, int I, int& i0, int& i1, float& w0
   i1 = (i0 < I - 1) ? i0 + 1 : i0;
 }
 
+// Stage a ROWS x COLS tile (origin (yo, xo), coordinates clamped to the map) into shared memory.
+//   dst = p[y][x]                         (pf == nullptr)
+//   dst = pf[y][mirror ? w-1-x : x]       (p == nullptr)
+//   dst = (p[y][x] + pf[y][w-1-x]) * 0.5  (both: flip averaging, model.py:90)
+template <int ROWS, int COLS, int NTHR>
+__device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float* __restrict__ p,
+                                           const float* __restrict__ pf, bool mirror, int yo, int xo, int h, int w,
+                                           int tid) {
+  constexpr int TOTAL = ROWS * COLS, BATCH = 8;
+#pragma unroll 1
+  for (int base = tid; base < TOTAL; base += NTHR * BATCH) {
+    float v[BATCH], f[BATCH];
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int i = base + u * NTHR;
+      v[u] = 0.f; f[u] = 0.f;
+      if (i < TOTAL) {
+        const int r = i / COLS, c = i - r * COLS;
+        const int y = clampi(yo + r, 0, h - 1), x = clampi(xo + c, 0, w - 1);
+        if (p) v[u] = __ldg(p + (size_t)y * w + x);
+        if (pf) f[u] = __ldg(pf + (size_t)y * w + (mirror ? w - 1 - x : x));
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < BATCH; ++u) {
+      const int i = base + u * NTHR;
+      if (i < TOTAL) dst[i] = (p && pf) ? __fmul_rn(__fadd_rn(v[u], f[u]), 0.5f) : (p ? v[u] : f[u]);
+    }
+  }
+}
+
 template <int E, int NW>
 __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -59,6 +90,7 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   int* sRowI1 = sRowI0 + SR;
   float* sRowW0 = (float*)(sRowI1 + SR);
   float* sRowW1 = sRowW0 + SR;
+  float* sNegInf = sRowW1 + SR;                  // [4] dummy row for lanes right of the image
 
   const ScaleDev& S = a.sc[0];
   const int tid = threadIdx.x;
@@ -72,39 +104,22 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   const int txo = x0 / 4 - 1, tyo = y0 / 4 - 1;     // origins of the tag tiles
 
   // ---------------- phase 1: stage inputs (clamped = replicated at the borders) ----------------
-  {
-    const float* p = S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc;
-    const float* pf = S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr;
-    for (int i = tid; i < LR * lc; i += nthr) {
-      const int r = i / lc, c = i - r * lc;
-      const int y = clampi(lyo + r, 0, S.lh - 1), x = clampi(lxo + c, 0, S.lw - 1);
-      float v = __ldg(p + (size_t)y * S.lw + x);
-      if (pf) v = __fmul_rn(__fadd_rn(v, __ldg(pf + (size_t)y * S.lw + (S.lw - 1 - x))), 0.5f);
-      sL[i] = v;
-    }
+  // Loads are issued in batches of 8 elements per thread before any is consumed, so a tile costs a
+  // handful of DRAM round trips instead of one per element.
+  stage_tile<LR, lc, nthr>(sL, S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc,
+                           S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr, true, lyo, lxo,
+                           S.lh, S.lw, tid);
+  stage_tile<SR, sc, nthr>(sS, S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc,
+                           S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr, true, hyo, hxo,
+                           S.hh, S.hw, tid);
+  stage_tile<TR, tc, nthr>(sT, a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc, nullptr, false, tyo, txo, a.th,
+                           a.tw, tid);
+  if (E > 1) {
+    const bool unflip = !a.tags_preflipped;   // model.py:93: flip(tag_f, W)[:, FLIP]
+    stage_tile<TR, tc, nthr>(sT + TR * tc, nullptr, a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc,
+                             unflip, tyo, txo, a.th, a.tw, tid);
   }
-  {
-    const float* p = S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc;
-    const float* pf = S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr;
-    for (int i = tid; i < SR * sc; i += nthr) {
-      const int r = i / sc, c = i - r * sc;
-      const int y = clampi(hyo + r, 0, S.hh - 1), x = clampi(hxo + c, 0, S.hw - 1);
-      float v = __ldg(p + (size_t)y * S.hw + x);
-      if (pf) v = __fmul_rn(__fadd_rn(v, __ldg(pf + (size_t)y * S.hw + (S.hw - 1 - x))), 0.5f);
-      sS[i] = v;
-    }
-  }
-#pragma unroll
-  for (int e = 0; e < E; ++e) {
-    const bool unflip = (e == 1) && !a.tags_preflipped;
-    const float* p = (e == 0) ? a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc
-                              : a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc;
-    for (int i = tid; i < TR * tc; i += nthr) {
-      const int r = i / tc, c = i - r * tc;
-      const int y = clampi(tyo + r, 0, a.th - 1), x = clampi(txo + c, 0, a.tw - 1);
-      sT[e * TR * tc + i] = __ldg(p + (size_t)y * a.tw + (unflip ? a.tw - 1 - x : x));
-    }
-  }
+  if (tid < 4) sNegInf[tid] = -INFINITY;
   if (tid < SR) {   // vertical taps of phase 2: half-res row -> rows of sL
     int i0, i1; float w0, w1;
     tap_x2(clampi(hyo + tid, 0, S.hh - 1), S.lh, i0, i1, w0, w1);
@@ -159,40 +174,48 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   __syncwarp();
 
   // ---------------- phase 3b: walk the rows, 4 columns per lane ------------------------------------
+  // Four rows per loop iteration so that the register windows (4 row-maxima rows, 2 value rows,
+  // 2 interpolated half-res rows) rotate by renaming instead of by moves.
   const int X0 = xw + 4 * lane;
   const bool active = X0 < W;
   {
-    const int sbase = 64 * warp + 2 * lane + 2;   // index of S[h0-1] in a tile row (even -> 8B aligned)
     const bool x_first = (X0 == 0);
     const float wa0 = x_first ? 1.f : 0.25f, wb0 = x_first ? 0.f : 0.75f;
+    const float NINF = -INFINITY;
+    // lanes right of the image read a dummy row of -inf (stride 0), which makes all their values -inf
+    const float* srow = active ? (sS + 64 * warp + 2 * lane + 2) : sNegInf;
+    const int sstride = active ? sc : 0;
     auto hpass = [&](int r, float (&h)[4]) {
-      const float2 p = *reinterpret_cast<const float2*>(sS + r * sc + sbase);
-      const float2 q = *reinterpret_cast<const float2*>(sS + r * sc + sbase + 2);
+      const float2 p = *reinterpret_cast<const float2*>(srow + r * sstride);
+      const float2 q = *reinterpret_cast<const float2*>(srow + r * sstride + 2);
       const float a0 = x_first ? p.y : p.x, b0 = x_first ? q.x : p.y;
       h[0] = fmaf(wa0, a0, __fmul_rn(wb0, b0));
       h[1] = fmaf(0.75f, p.y, __fmul_rn(0.25f, q.x));
       h[2] = fmaf(0.25f, p.y, __fmul_rn(0.75f, q.x));
       h[3] = fmaf(0.75f, q.x, __fmul_rn(0.25f, q.y));
     };
-    float hA[4], hB[4], hC[4];
+    float hA[4], hB[4], hC[4], hD[4];
     hpass(0, hA);
     hpass(1, hB);
-    // register windows: rm = row maxima of rows y-4..y-1 (r0 oldest), vq = values of rows y-2, y-1
+    // register windows: r0..r3 = row maxima of rows y-4..y-1, vq0 / vq1 = values of rows y-2 / y-1
     float r0[4], r1[4], r2[4], r3[4], vq0[4], vq1[4];
 #pragma unroll
-    for (int c = 0; c < 4; ++c) { r0[c] = r1[c] = r2[c] = r3[c] = -INFINITY; vq0[c] = vq1[c] = -INFINITY; }
-    float* hm_plane = a.agg_hm + ((size_t)b * a.K + k) * H * W;
-    const size_t wplane = ((size_t)b * a.K + k) * H * a.wpr;
+    for (int c = 0; c < 4; ++c) { r0[c] = r1[c] = r2[c] = r3[c] = NINF; vq0[c] = vq1[c] = NINF; }
+    float* const hm_plane = a.agg_hm + ((size_t)b * a.K + k) * H * W + X0;
+    const size_t wbase = ((size_t)b * a.K + k) * H * a.wpr + (X0 >> 5);
+    const bool word_writer = active && (lane & 7) == 0;
+    const int shl = 4 * (lane & 7);
 
-    auto process_row = [&](int y, int slot, const float (&v)[4]) {
-      // v: values of row y (-inf if the row or the columns are outside the image)
-      if (active && y >= y0 && y < y0 + RB && y < H)
-        *reinterpret_cast<float4*>(hm_plane + (size_t)y * W + X0) = make_float4(v[0], v[1], v[2], v[3]);
+    // t = index of the row in the walk (row y = ys + t); rows outside the image carry -inf
+    auto process_row = [&](int t, const float (&v)[4]) {
+      const int y = ys + t;
+      if (t >= 2 && t < RB + 2 && y < H && active)
+        *reinterpret_cast<float4*>(hm_plane + (size_t)y * W) = make_float4(v[0], v[1], v[2], v[3]);
       // 5-wide row maximum: own 4 + 2 from each neighbour lane (halo columns for lanes 0 / 31)
       float l2 = __shfl_up_sync(kFull, v[2], 1), l3 = __shfl_up_sync(kFull, v[3], 1);
       float q0 = __shfl_down_sync(kFull, v[0], 1), q1 = __shfl_down_sync(kFull, v[1], 1);
-      if (lane == 0) { l2 = edge[slot * 4 + 0]; l3 = edge[slot * 4 + 1]; }
-      if (lane == 31) { q0 = edge[slot * 4 + 2]; q1 = edge[slot * 4 + 3]; }
+      if (lane == 0) { const float2 e = *reinterpret_cast<const float2*>(edge + t * 4); l2 = e.x; l3 = e.y; }
+      if (lane == 31) { const float2 e = *reinterpret_cast<const float2*>(edge + t * 4 + 2); q0 = e.x; q1 = e.y; }
       const float pb = fmaxf(v[0], v[1]), pc = fmaxf(v[2], v[3]);
       float rm[4];
       rm[0] = max3(fmaxf(l2, l3), pb, v[2]);
@@ -201,27 +224,24 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
       rm[3] = max3(v[1], pc, fmaxf(q0, q1));
       // centre row yc = y - 2: 5-tall column maximum over rows y-4..y
       const int yc = y - 2;
-      if (yc >= y0 && yc < y0 + RB && yc < H) {   // uniform over the CTA
-        float hm4 = -INFINITY, wm4 = -INFINITY;
-        unsigned nib = 0;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          const float m = max3(max3(r0[c], r1[c], r2[c]), r3[c], rm[c]);
-          const float vc = vq0[c];
-          const bool keep = active && (m == vc);
-          const float nv = keep ? vc : __fmul_rn(vc, 0.0f);
-          nib |= keep ? (1u << c) : 0u;
-          if (active) { hm4 = fmaxf(hm4, vc); wm4 = fmaxf(wm4, nv); }
-        }
-        unsigned bits = nib << (4 * (lane & 7));
+      if (t >= 4 && yc < H) {   // uniform over the CTA
+        const float m0 = max3(max3(r0[0], r1[0], r2[0]), r3[0], rm[0]);
+        const float m1 = max3(max3(r0[1], r1[1], r2[1]), r3[1], rm[1]);
+        const float m2 = max3(max3(r0[2], r1[2], r2[2]), r3[2], rm[2]);
+        const float m3 = max3(max3(r0[3], r1[3], r2[3]), r3[3], rm[3]);
+        const bool k0 = (m0 == vq0[0]), k1 = (m1 == vq0[1]), k2 = (m2 == vq0[2]), k3 = (m3 == vq0[3]);
+        // NMS'd value of a suppressed pixel is +-0; its sign cannot change any comparison made on the word maximum
+        float wm4 = fmaxf(fmaxf(k0 ? vq0[0] : 0.f, k1 ? vq0[1] : 0.f), fmaxf(k2 ? vq0[2] : 0.f, k3 ? vq0[3] : 0.f));
+        float hm4 = fmaxf(fmaxf(vq0[0], vq0[1]), fmaxf(vq0[2], vq0[3]));
+        unsigned bits = ((k0 ? 1u : 0u) | (k1 ? 2u : 0u) | (k2 ? 4u : 0u) | (k3 ? 8u : 0u)) << shl;
 #pragma unroll
         for (int o = 1; o < 8; o <<= 1) {
           bits |= __shfl_xor_sync(kFull, bits, o);
           hm4 = fmaxf(hm4, __shfl_xor_sync(kFull, hm4, o));
           wm4 = fmaxf(wm4, __shfl_xor_sync(kFull, wm4, o));
         }
-        if ((lane & 7) == 0 && active) {
-          const size_t w = wplane + (size_t)yc * a.wpr + (X0 >> 5);
+        if (word_writer) {
+          const size_t w = wbase + (size_t)yc * a.wpr;
           a.mask[w] = bits;
           a.wmax[w] = wm4;
           a.hmax[w] = hm4;
@@ -235,21 +255,54 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
     };
 
 #pragma unroll 1
-    for (int p = 0; p < NROWS / 2; ++p) {
-      const int ye = ys + 2 * p;
-      hpass(p + 2, hC);
-      float ve[4], vo[4];
-      const bool e_in = active && ye >= 0 && ye < H, o_in = active && ye + 1 >= 0 && ye + 1 < H;
+    for (int it = 0; it < NROWS / 4; ++it) {
+      const int t = 4 * it, y = ys + t;            // y = 2 (mod 4); half-res rows j-1..j+2 = tile rows 2it..2it+3
+      hpass(2 * it + 2, hC);
+      hpass(2 * it + 3, hD);
+      float v[4];
+      // row y (even): taps (hA, hB)
+      if (y >= 0 && y < H) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        const float t0 = (ye == 0) ? fmaf(1.f, hB[c], __fmul_rn(0.f, hC[c])) : fmaf(0.25f, hA[c], __fmul_rn(0.75f, hB[c]));
-        ve[c] = e_in ? t0 : -INFINITY;
-        vo[c] = o_in ? fmaf(0.75f, hB[c], __fmul_rn(0.25f, hC[c])) : -INFINITY;
+        for (int c = 0; c < 4; ++c) v[c] = fmaf(0.25f, hA[c], __fmul_rn(0.75f, hB[c]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = NINF;
       }
-      process_row(ye, 2 * p, ve);
-      process_row(ye + 1, 2 * p + 1, vo);
+      process_row(t, v);
+      // row y+1 (odd): taps (hB, hC)
+      if (y + 1 >= 0 && y + 1 < H) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { hA[c] = hB[c]; hB[c] = hC[c]; }
+        for (int c = 0; c < 4; ++c) v[c] = fmaf(0.75f, hB[c], __fmul_rn(0.25f, hC[c]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = NINF;
+      }
+      process_row(t + 1, v);
+      // row y+2 (even): taps (hB, hC); the first image row clamps to (row 0, row 1) with weights (1, 0)
+      if (y + 2 < H) {
+        if (y + 2 == 0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[c] = fmaf(1.f, hC[c], __fmul_rn(0.f, hD[c]));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[c] = fmaf(0.25f, hB[c], __fmul_rn(0.75f, hC[c]));
+        }
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = NINF;
+      }
+      process_row(t + 2, v);
+      // row y+3 (odd): taps (hC, hD)
+      if (y + 3 < H) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = fmaf(0.75f, hC[c], __fmul_rn(0.25f, hD[c]));
+      } else {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = NINF;
+      }
+      process_row(t + 3, v);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { hA[c] = hC[c]; hB[c] = hD[c]; }
     }
   }
 
