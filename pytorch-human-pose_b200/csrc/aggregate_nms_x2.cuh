@@ -47,33 +47,44 @@ __device__ __forceinline__ void tap_x2(int o, int I, int& i0, int& i1, float& w0
   i1 = (i0 < I - 1) ? i0 + 1 : i0;
 }
 
-// Stage a ROWS x COLS tile (origin (yo, xo), coordinates clamped to the map) into shared memory.
-//   dst = p[y][x]                         (pf == nullptr)
-//   dst = pf[y][mirror ? w-1-x : x]       (p == nullptr)
-//   dst = (p[y][x] + pf[y][w-1-x]) * 0.5  (both: flip averaging, model.py:90)
-template <int ROWS, int COLS, int NTHR>
+// Stage a ROWS x COLS tile (origin (yo, xo), coordinates clamped to the map = border replication)
+// into shared memory.  One warp per tile row (lanes along x: coalesced), two rows per batch so that
+// 2 * ceil(COLS/32) independent loads per operand are in flight before the first one is consumed.
+//   MODE 0: dst = p[y][x]      MODE 1: dst = pf[y][mirror ? w-1-x : x]
+//   MODE 2: dst = (p[y][x] + pf[y][w-1-x]) * 0.5   (flip averaging, model.py:90)
+template <int MODE, int ROWS, int COLS, int NW>
 __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float* __restrict__ p,
                                            const float* __restrict__ pf, bool mirror, int yo, int xo, int h, int w,
-                                           int tid) {
-  constexpr int TOTAL = ROWS * COLS, BATCH = 8;
+                                           int warp, int lane) {
+  constexpr int NIT = (COLS + 31) / 32, RPB = 2;
+  const int xm = w - 1;
 #pragma unroll 1
-  for (int base = tid; base < TOTAL; base += NTHR * BATCH) {
-    float v[BATCH], f[BATCH];
+  for (int r0 = warp * RPB; r0 < ROWS; r0 += NW * RPB) {
+    float v[RPB][NIT], f[RPB][NIT];
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u) {
-      const int i = base + u * NTHR;
-      v[u] = 0.f; f[u] = 0.f;
-      if (i < TOTAL) {
-        const int r = i / COLS, c = i - r * COLS;
-        const int y = clampi(yo + r, 0, h - 1), x = clampi(xo + c, 0, w - 1);
-        if (p) v[u] = __ldg(p + (size_t)y * w + x);
-        if (pf) f[u] = __ldg(pf + (size_t)y * w + (mirror ? w - 1 - x : x));
+    for (int j = 0; j < RPB; ++j) {
+      const int r = r0 + j;
+      const size_t row = (size_t)clampi(yo + r, 0, h - 1) * w;
+#pragma unroll
+      for (int u = 0; u < NIT; ++u) {
+        const int c = lane + 32 * u;
+        v[j][u] = 0.f; f[j][u] = 0.f;
+        if (r < ROWS && c < COLS) {
+          const int x = clampi(xo + c, 0, xm);
+          if (MODE != 1) v[j][u] = __ldg(p + row + x);
+          if (MODE != 0) f[j][u] = __ldg(pf + row + ((MODE == 2 || mirror) ? xm - x : x));
+        }
       }
     }
 #pragma unroll
-    for (int u = 0; u < BATCH; ++u) {
-      const int i = base + u * NTHR;
-      if (i < TOTAL) dst[i] = (p && pf) ? __fmul_rn(__fadd_rn(v[u], f[u]), 0.5f) : (p ? v[u] : f[u]);
+    for (int j = 0; j < RPB; ++j) {
+      const int r = r0 + j;
+#pragma unroll
+      for (int u = 0; u < NIT; ++u) {
+        const int c = lane + 32 * u;
+        if (r < ROWS && c < COLS)
+          dst[r * COLS + c] = (MODE == 2) ? __fmul_rn(__fadd_rn(v[j][u], f[j][u]), 0.5f) : (MODE == 0 ? v[j][u] : f[j][u]);
+      }
     }
   }
 }
@@ -103,21 +114,23 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   const int lxo = x0 / 4 - 2, lyo = y0 / 4 - 2;     // origins of the quarter-res hm tile
   const int txo = x0 / 4 - 1, tyo = y0 / 4 - 1;     // origins of the tag tiles
 
-  // ---------------- phase 1: stage inputs (clamped = replicated at the borders) ----------------
-  // Loads are issued in batches of 8 elements per thread before any is consumed, so a tile costs a
-  // handful of DRAM round trips instead of one per element.
-  stage_tile<LR, lc, nthr>(sL, S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc,
-                           S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr, true, lyo, lxo,
-                           S.lh, S.lw, tid);
-  stage_tile<SR, sc, nthr>(sS, S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc,
-                           S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr, true, hyo, hxo,
-                           S.hh, S.hw, tid);
-  stage_tile<TR, tc, nthr>(sT, a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc, nullptr, false, tyo, txo, a.th,
-                           a.tw, tid);
-  if (E > 1) {
-    const bool unflip = !a.tags_preflipped;   // model.py:93: flip(tag_f, W)[:, FLIP]
-    stage_tile<TR, tc, nthr>(sT + TR * tc, nullptr, a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc,
-                             unflip, tyo, txo, a.th, a.tw, tid);
+  // ---------------- phase 1: stage inputs ----------------------------------------------------------
+  {
+    const float* lo = S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc;
+    const float* hi = S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc;
+    if (S.lo_f) {
+      stage_tile<2, LR, lc, NW>(sL, lo, S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc, true, lyo, lxo, S.lh, S.lw, warp, lane);
+      stage_tile<2, SR, sc, NW>(sS, hi, S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc, true, hyo, hxo, S.hh, S.hw, warp, lane);
+    } else {
+      stage_tile<0, LR, lc, NW>(sL, lo, nullptr, false, lyo, lxo, S.lh, S.lw, warp, lane);
+      stage_tile<0, SR, sc, NW>(sS, hi, nullptr, false, hyo, hxo, S.hh, S.hw, warp, lane);
+    }
+    stage_tile<0, TR, tc, NW>(sT, a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc, nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
+    if (E > 1) {
+      const bool unflip = !a.tags_preflipped;   // model.py:93: flip(tag_f, W)[:, FLIP]
+      stage_tile<1, TR, tc, NW>(sT + TR * tc, nullptr, a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc,
+                                unflip, tyo, txo, a.th, a.tw, warp, lane);
+    }
   }
   if (tid < 4) sNegInf[tid] = -INFINITY;
   if (tid < SR) {   // vertical taps of phase 2: half-res row -> rows of sL
