@@ -210,7 +210,19 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
       for (int q = 0; q < cnt; ++q) {
         const unsigned long long bq = __shfl_sync(kFull, best, q);
         if (hw_o < (unsigned)(bq >> 32)) continue;
-        const float v = refine_value(pv, t0, t1, __shfl_sync(kFull, T0, q), __shfl_sync(kFull, T1, q), E);
+        const float Tq0 = __shfl_sync(kFull, T0, q), Tq1 = __shfl_sync(kFull, T1, q);
+        {
+          // cheap screen: value = pv - rint(d) can reach the running best b only if rint(d) <= pv - b,
+          // i.e. d <= floor(pv - b) + 0.5; compared on squared distances with a relative slack that
+          // dwarfs the rounding of the exact evaluation below (a false positive only costs time).
+          const float dv = pv - unordered_f32((unsigned)(bq >> 32));
+          const float R = floorf(dv + fabsf(dv) * 1e-6f);
+          const float a0 = t0 - Tq0, a1 = t1 - Tq1;
+          const float s = a0 * a0 + (E > 1 ? a1 * a1 : 0.f);
+          const float lim = (R + 0.5f) * (R + 0.5f) * 1.0001f + 1e-30f;
+          if (!__any_sync(kFull, valid && R >= 0.f && !(s > lim))) continue;
+        }
+        const float v = refine_value(pv, t0, t1, Tq0, Tq1, E);
         const unsigned long long key = valid ? pack_key(v, idx) : 0ull;
         const unsigned hi = __reduce_max_sync(kFull, (unsigned)(key >> 32));
         const unsigned lo = __reduce_max_sync(kFull, ((unsigned)(key >> 32) == hi) ? (unsigned)key : 0u);

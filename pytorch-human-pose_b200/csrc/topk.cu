@@ -89,11 +89,165 @@ __device__ __forceinline__ void sort_heap(HeapRef h, int len) {
   }
 }
 
+// ---- exact sink: the libstdc++ heap in shared memory, edited by lane 0 -----------------------------
+struct HeapSink {
+  HeapRef h;
+  int M, lane;
+  float top;
+  __device__ __forceinline__ void init(float nv) {   // lane < M holds element `lane` of the row
+    if (lane < M) { h.v[lane] = nv; h.i[lane] = lane; }
+    __syncwarp();
+    if (lane == 0) make_heap(h, M);
+    __syncwarp();
+    top = h.v[0];
+  }
+  __device__ __forceinline__ void insert(float cv, int idx) {   // std::__heap_select: __pop_heap(first, middle, i)
+    if (lane == 0) adjust_heap(h, 0, M, cv, idx);
+    __syncwarp();
+    top = h.v[0];
+  }
+};
+
+// ---- fast sink: the M kept elements sorted by value across the lanes of the warp ---------------------
+// The heap's VALUE dynamics do not depend on its arrangement (an element enters iff it is strictly
+// greater than the smallest kept value, and a smallest-valued element leaves), so a sorted register
+// array evolves through the same multisets.  Which of several EQUAL elements leaves, and the final
+// order of equal elements, is where the heap arrangement matters; `ambiguous()` detects every such
+// case (two equal values among the final M, or an evicted value equal to the final minimum -- the
+// +-0 tail of a channel with fewer than M positive peaks always lands here) and the row is then
+// replayed with the exact sink.  Otherwise the result (distinct values, descending) is what
+// sort_heap produces from any arrangement.
+struct SortedSink {
+  int M, lane;
+  float sv;       // lane i < M: i-th largest kept value (lanes >= M: -inf)
+  int si;
+  float top;      // smallest kept value
+  float evicted;  // value of the last evicted element (evictions are non-decreasing)
+  bool any_evicted;
+  __device__ __forceinline__ void init(float nv) {
+    sv = lane < M ? nv : -INFINITY;
+    si = lane;
+    // bitonic sort, descending by value
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+      for (int j = k >> 1; j > 0; j >>= 1) {
+        const float ov = __shfl_xor_sync(kFull, sv, j);
+        const int oi = __shfl_xor_sync(kFull, si, j);
+        const bool up = ((lane & k) == 0);          // this k-block sorts descending
+        const bool lower = ((lane & j) == 0);       // this lane keeps the larger (if up) element
+        const bool take = (lower == up) ? (ov > sv) : (ov < sv);
+        if (take) { sv = ov; si = oi; }
+      }
+    }
+    top = __shfl_sync(kFull, sv, M - 1);
+    evicted = -INFINITY;
+    any_evicted = false;
+  }
+  __device__ __forceinline__ void insert(float cv, int idx) {   // requires cv > top
+    const int pos = __popc(__ballot_sync(kFull, lane < M && sv >= cv));
+    const float uv = __shfl_up_sync(kFull, sv, 1);
+    const int ui = __shfl_up_sync(kFull, si, 1);
+    evicted = top;
+    any_evicted = true;
+    if (lane < M) {
+      if (lane > pos) { sv = uv; si = ui; }
+      else if (lane == pos) { sv = cv; si = idx; }
+    }
+    top = __shfl_sync(kFull, sv, M - 1);
+  }
+  __device__ __forceinline__ bool ambiguous() const {
+    const float nxt = __shfl_down_sync(kFull, sv, 1);
+    const bool tie = __ballot_sync(kFull, lane < M - 1 && sv == nxt) != 0u;
+    return tie || (any_evicted && evicted == top);
+  }
+};
+
+// Stream one row through a sink in index order.  The per-word maxima are scanned 128 words at a time
+// (the next 128 are prefetched while this group is processed); words that can still hold an
+// entering element are expanded up to 8 at a time so that their heatmap lines and mask words are
+// fetched together instead of one DRAM round trip each.
+template <typename Sink>
+__device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ hm, const uint32_t* __restrict__ mk,
+                                         const float* __restrict__ wm, int H, int W, int wpr, int M, int lane) {
+  {
+    float nv = 0.f;
+    if (lane < M) {
+      const int y = lane / W, x = lane % W;
+      const float v = hm[lane];
+      const bool keep = (mk[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+      nv = keep ? v : __fmul_rn(v, 0.0f);
+    }
+    sink.init(nv);
+  }
+  const int nwords = H * wpr;
+  constexpr int kGroup = 4, kSlots = 8;
+  float nxt[kGroup];
+#pragma unroll
+  for (int u = 0; u < kGroup; ++u) {
+    const int wd = 32 * u + lane;
+    nxt[u] = wd < nwords ? wm[wd] : -INFINITY;
+  }
+  for (int base = 0; base < nwords; base += 32 * kGroup) {
+    float cur[kGroup];
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      cur[u] = nxt[u];
+      const int wd = base + 32 * (kGroup + u) + lane;
+      nxt[u] = wd < nwords ? wm[wd] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      const int cbase = base + 32 * u;
+      uint32_t pass = __ballot_sync(kFull, cur[u] > sink.top);
+      while (pass) {
+        float hv[kSlots];
+        uint32_t mw[kSlots];
+        int wl[kSlots];
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+          wl[s] = -1;
+          hv[s] = 0.f;
+          mw[s] = 0u;
+          if (pass) {
+            const int l = __ffs(pass) - 1;
+            pass &= pass - 1;
+            wl[s] = l;
+            const int w2 = cbase + l;
+            const int y = w2 / wpr, x = (w2 - y * wpr) * 32 + lane;
+            const int idx = y * W + x;
+            if (x < W && idx >= M) hv[s] = hm[idx];
+            mw[s] = mk[w2];
+          }
+        }
+#pragma unroll
+        for (int s = 0; s < kSlots; ++s) {
+          if (wl[s] < 0) break;
+          if (!(__shfl_sync(kFull, cur[u], wl[s]) > sink.top)) continue;   // the top may have risen meanwhile
+          const int w2 = cbase + wl[s];
+          const int y = w2 / wpr, x0 = (w2 - y * wpr) * 32;
+          const bool valid = (x0 + lane < W) && (y * W + x0 + lane >= M);
+          const bool keep = (mw[s] >> lane) & 1u;
+          const float nv = keep ? hv[s] : __fmul_rn(hv[s], 0.0f);
+          uint32_t cand = __ballot_sync(kFull, valid && nv > sink.top);
+          while (cand) {
+            const int j = __ffs(cand) - 1;
+            cand &= cand - 1;
+            const float cv = __shfl_sync(kFull, nv, j);
+            if (cv > sink.top) sink.insert(cv, y * W + x0 + j);
+          }
+        }
+      }
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __restrict__ agg_hm,
                                                               const float* __restrict__ agg_tags,
                                                               const uint32_t* __restrict__ mask,
                                                               const float* __restrict__ wmax, int rows, int H, int W,
-                                                              int wpr, int E, int M, float* __restrict__ scores_k,
+                                                              int wpr, int E, int M, int force_exact,
+                                                              float* __restrict__ scores_k,
                                                               int32_t* __restrict__ idx_k,
                                                               int32_t* __restrict__ coords_k,
                                                               float* __restrict__ tags_k) {
@@ -105,61 +259,33 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __re
   const float* hm = agg_hm + (size_t)row * H * W;
   const uint32_t* mk = mask + (size_t)row * H * wpr;
   const float* wm = wmax + (size_t)row * H * wpr;
-  HeapRef h{s_v[warp], s_i[warp]};
 
-  // heap <- first M elements of the row (their NMS'd values)
-  if (lane < M) {
-    const int y = lane / W, x = lane % W;
-    const float v = hm[lane];
-    const bool keep = (mk[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
-    h.v[lane] = keep ? v : __fmul_rn(v, 0.0f);
-    h.i[lane] = lane;
+  float out_v = 0.f;
+  int out_i = 0;
+  bool done = false;
+  if (!force_exact) {
+    SortedSink fast;
+    fast.M = M; fast.lane = lane;
+    scan_row(fast, hm, mk, wm, H, W, wpr, M, lane);
+    if (!fast.ambiguous()) { out_v = fast.sv; out_i = fast.si; done = true; }
   }
-  __syncwarp();
-  if (lane == 0) make_heap(h, M);
-  __syncwarp();
-  float top = h.v[0];
-
-  const int nwords = H * wpr;
-  for (int base = 0; base < nwords; base += 32) {
-    const int wd = base + lane;
-    const float wv = wd < nwords ? wm[wd] : -INFINITY;
-    uint32_t pass = __ballot_sync(kFull, wv > top);
-    while (pass) {
-      const int l = __ffs(pass) - 1;
-      pass &= pass - 1;
-      if (!(__shfl_sync(kFull, wv, l) > top)) continue;   // the top may have risen meanwhile
-      const int w2 = base + l;
-      const int y = w2 / wpr, x = (w2 % wpr) * 32 + lane;
-      const int idx = y * W + x;
-      const bool valid = (x < W) && (idx >= M);
-      const float v = valid ? hm[idx] : 0.f;
-      const bool keep = (mk[w2] >> lane) & 1u;
-      const float nv = keep ? v : __fmul_rn(v, 0.0f);
-      uint32_t cand = __ballot_sync(kFull, valid && nv > top);
-      while (cand) {
-        const int j = __ffs(cand) - 1;
-        cand &= cand - 1;
-        const float cv = __shfl_sync(kFull, nv, j);
-        if (cv > top) {   // std::__heap_select: comp(i, first) -> __pop_heap(first, middle, i)
-          if (lane == 0) adjust_heap(h, 0, M, cv, y * W + (w2 % wpr) * 32 + j);
-          __syncwarp();
-          top = h.v[0];
-        }
-      }
-    }
+  if (!done) {   // ties in play: replay the row with the exact libstdc++ heap
+    HeapSink exact;
+    exact.h = HeapRef{s_v[warp], s_i[warp]};
+    exact.M = M; exact.lane = lane;
+    scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
+    __syncwarp();
+    if (lane == 0) sort_heap(exact.h, M);
+    __syncwarp();
+    if (lane < M) { out_v = exact.h.v[lane]; out_i = exact.h.i[lane]; }
   }
-  __syncwarp();
-  if (lane == 0) sort_heap(h, M);
-  __syncwarp();
   if (lane < M) {
-    const int idx = h.i[lane];
     const size_t o = (size_t)row * M + lane;
-    scores_k[o] = h.v[lane];
-    idx_k[o] = idx;
-    coords_k[o * 2 + 0] = idx % W;
-    coords_k[o * 2 + 1] = idx / W;
-    for (int e = 0; e < E; ++e) tags_k[o * E + e] = agg_tags[((size_t)row * H * W + idx) * E + e];
+    scores_k[o] = out_v;
+    idx_k[o] = out_i;
+    coords_k[o * 2 + 0] = out_i % W;
+    coords_k[o * 2 + 1] = out_i / W;
+    for (int e = 0; e < E; ++e) tags_k[o * E + e] = agg_tags[((size_t)row * H * W + out_i) * E + e];
   }
 }
 
@@ -175,7 +301,7 @@ int launch_topk(const HpdParams* p, const HpdBuffers* buf, cudaStream_t st) {
   const int wpr = (p->out_w + 31) / 32;
   topk_kernel<<<(rows + kTopkWarps - 1) / kTopkWarps, kTopkWarps * 32, 0, st>>>(
       buf->agg_hm, buf->agg_tags, buf->nms_mask, buf->nms_wmax, rows, p->out_h, p->out_w, wpr, p->emb, p->max_people,
-      buf->scores_k, buf->idx_k, buf->coords_k, buf->tags_k);
+      p->force_generic, buf->scores_k, buf->idx_k, buf->coords_k, buf->tags_k);
   count_launch();
   return check_launch("topk_kernel");
 }

@@ -169,3 +169,28 @@ def test_decode_matches_committed_reference_goldens(name):
     gj, ps = res.to_numpy()[0]
     assert gj.dtype == g["grouped_joints"].dtype
     assert np.array_equal(gj, g["grouped_joints"]) and np.array_equal(ps, g["person_scores"])
+
+
+@pytest.mark.parametrize("gen,kw,size", [
+    ("netlike", dict(batch=2, size=256, flip=True, seed=61), 256),
+    ("crowd", dict(batch=2, size=256, persons=25, flip=True, seed=62, quantised=True), 256),
+    ("crowd", dict(batch=1, size=512, persons=30, flip=False, seed=63, quantised=True), 512),
+    ("netlike", dict(batch=1, size=512, flip=True, seed=64, negative_channels=(0, 1, 2, 3)), 512),
+])
+def test_topk_fast_path_equals_exact_heap_replay(gen, kw, size):
+    """The sorted-register fast path (with its ambiguity detector) against the forced libstdc++-heap path."""
+    from hpdecode import ops
+    scales = _dev(getattr(synth, gen)(**kw))
+    B = kw["batch"]
+    E = 2 if kw["flip"] else 1
+    outs = []
+    for force in (0, 1):
+        bufs = ops.DecodeBuffers(B, 17, size, size, E, 30, "cuda:0")
+        p = ops.make_params(B, 17, size, size, E, 30, 0.05, 0.5)
+        p.force_generic = force
+        ops.run_stage("aggregate_nms", bufs, p, scales=scales)
+        ops.run_stage("topk", bufs, p)
+        torch.cuda.synchronize()
+        outs.append((bufs.idx_k.cpu().numpy(), bufs.scores_k.cpu().numpy(), bufs.tags_k.cpu().numpy()))
+    assert np.array_equal(outs[0][0], outs[1][0])
+    assert np.array_equal(_bits(outs[0][1]), _bits(outs[1][1])) and np.array_equal(_bits(outs[0][2]), _bits(outs[1][2]))
