@@ -158,10 +158,16 @@ __global__ void adjust_prepare_kernel(const float* __restrict__ agg_hm, const fl
 constexpr int kScanWarps = 4;
 constexpr int kScanWordsPerBlock = 1024;
 
+// pass 0 expands only words whose raw maximum reaches the joint's M-th top-k score (the words around
+// the strongest peaks), pass 1 the rest.  Running bests are shared through global memory (re-read at
+// every 32-word chunk, published as soon as they improve), so after pass 0 almost every remaining
+// word is pruned by its maximum instead of being climbed flank by flank in index order.
 __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const float* __restrict__ agg_hm,
                                                                       const float* __restrict__ agg_tags,
-                                                                      const float* __restrict__ hmax, int K, int M,
-                                                                      int E, int H, int W, int wpr, RefineWs ws) {
+                                                                      const float* __restrict__ hmax,
+                                                                      const float* __restrict__ scores_k, int pass_id,
+                                                                      int K, int M, int E, int H, int W, int wpr,
+                                                                      RefineWs ws) {
   const int bk = blockIdx.y;
   const int cnt = ws.miss_cnt[bk];
   if (cnt == 0) return;
@@ -174,6 +180,8 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
   const float* m = agg_hm + (size_t)bk * H * W;
   const float* t = agg_tags + (size_t)bk * H * W * E;
   const float* hx = hmax + (size_t)bk * nwords;
+  const float split = scores_k[(size_t)bk * M + M - 1];
+  unsigned long long* gkeys = ws.keys + (size_t)bk * M;
 
   // lane q < cnt tracks listed pair q
   float T0 = 0.f, T1 = 0.f;
@@ -182,57 +190,52 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
     const int p = ws.miss_pid[(size_t)bk * M + lane];
     T0 = ws.T[((size_t)b * M + p) * 2 + 0];
     T1 = ws.T[((size_t)b * M + p) * 2 + 1];
-    best = ws.keys[(size_t)bk * M + lane];
   }
-  const unsigned long long best_in = best;
-  // a word matters if its raw maximum can reach the smallest running best among the pairs
-  unsigned thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
 
   for (int base = w_begin; base < w_end; base += 32) {
     const int wd = base + lane;
     const float hv = wd < w_end ? hx[wd] : -INFINITY;
-    uint32_t pass = __ballot_sync(kFull, wd < w_end && ordered_u32(__fadd_rn(hv, 0.0f)) >= thr);
+    if (lane < cnt) best = __ldcg(gkeys + lane);           // newest bests of all warps working on this joint
+    // a word matters if its raw maximum can reach the smallest running best among the pairs
+    unsigned thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
+    const bool mine = (pass_id == 0) ? (hv >= split) : !(hv >= split);
+    uint32_t pass = __ballot_sync(kFull, wd < w_end && mine && ordered_u32(__fadd_rn(hv, 0.0f)) >= thr);
     while (pass) {
       const int l = __ffs(pass) - 1;
       pass &= pass - 1;
       const unsigned hw_o = ordered_u32(__fadd_rn(__shfl_sync(kFull, hv, l), 0.0f));
       if (hw_o < thr) continue;
       const int w2 = base + l;
-      const int y = w2 / wpr, x = (w2 % wpr) * 32 + lane;
-      const bool valid = x < W;
-      const int idx = y * W + x;
+      const int y = w2 / wpr, x0 = (w2 - y * wpr) * 32;
+      const bool valid = x0 + lane < W;
+      const int idx = y * W + x0 + lane;
       float pv = 0.f, t0 = 0.f, t1 = 0.f;
       if (valid) {
         pv = m[idx];
         t0 = t[(size_t)idx * E];
         if (E > 1) t1 = t[(size_t)idx * E + 1];
       }
+      bool improved = false;
       for (int q = 0; q < cnt; ++q) {
         const unsigned long long bq = __shfl_sync(kFull, best, q);
         if (hw_o < (unsigned)(bq >> 32)) continue;
-        const float Tq0 = __shfl_sync(kFull, T0, q), Tq1 = __shfl_sync(kFull, T1, q);
-        {
-          // cheap screen: value = pv - rint(d) can reach the running best b only if rint(d) <= pv - b,
-          // i.e. d <= floor(pv - b) + 0.5; compared on squared distances with a relative slack that
-          // dwarfs the rounding of the exact evaluation below (a false positive only costs time).
-          const float dv = pv - unordered_f32((unsigned)(bq >> 32));
-          const float R = floorf(dv + fabsf(dv) * 1e-6f);
-          const float a0 = t0 - Tq0, a1 = t1 - Tq1;
-          const float s = a0 * a0 + (E > 1 ? a1 * a1 : 0.f);
-          const float lim = (R + 0.5f) * (R + 0.5f) * 1.0001f + 1e-30f;
-          if (!__any_sync(kFull, valid && R >= 0.f && !(s > lim))) continue;
+        const float v = refine_value(pv, t0, t1, __shfl_sync(kFull, T0, q), __shfl_sync(kFull, T1, q), E);
+        const unsigned vo = valid ? ordered_u32(v) : 0u;
+        if (!__any_sync(kFull, vo >= (unsigned)(bq >> 32))) continue;
+        const unsigned hi = __reduce_max_sync(kFull, vo);
+        const int first = __ffs(__ballot_sync(kFull, vo == hi)) - 1;      // lowest index among equal values
+        const unsigned long long wbest = ((unsigned long long)hi << 32) | (unsigned)(~(unsigned)(y * W + x0 + first));
+        if (wbest > bq) {
+          if (lane == q) best = wbest;
+          improved = true;
         }
-        const float v = refine_value(pv, t0, t1, Tq0, Tq1, E);
-        const unsigned long long key = valid ? pack_key(v, idx) : 0ull;
-        const unsigned hi = __reduce_max_sync(kFull, (unsigned)(key >> 32));
-        const unsigned lo = __reduce_max_sync(kFull, ((unsigned)(key >> 32) == hi) ? (unsigned)key : 0u);
-        const unsigned long long wbest = ((unsigned long long)hi << 32) | lo;
-        if (lane == q && wbest > best) best = wbest;
       }
-      thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
+      if (improved) {
+        if (lane < cnt) atomicMax(gkeys + lane, best);
+        thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
+      }
     }
   }
-  if (lane < cnt && best > best_in) atomicMax(&ws.keys[(size_t)bk * M + lane], best);
 }
 
 __global__ void refine_apply_kernel(const float* __restrict__ agg_hm, int total, int K, int M, int E, int H, int W,
@@ -264,9 +267,9 @@ size_t refine_workspace_bytes(const HpdParams* p) {
 }
 
 int launch_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* wsp, size_t ws_bytes, cudaStream_t st) {
-  if (!buf->agg_hm || !buf->agg_tags || !buf->hm_wmax || !buf->idx_k || !buf->poses || !buf->person_scores ||
-      !buf->n_person) {
-    set_error("hpd_adjust_refine: agg_hm, agg_tags, hm_wmax, idx_k, poses, person_scores, n_person are required");
+  if (!buf->agg_hm || !buf->agg_tags || !buf->hm_wmax || !buf->idx_k || !buf->scores_k || !buf->poses ||
+      !buf->person_scores || !buf->n_person) {
+    set_error("hpd_adjust_refine: agg_hm, agg_tags, hm_wmax, idx_k, scores_k, poses, person_scores, n_person are required");
     return HPD_EINVAL;
   }
   if (!wsp || ws_bytes < refine_workspace_bytes(p)) {
@@ -287,10 +290,12 @@ int launch_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* wsp, s
   if (rc || !p->do_refine) return rc;
   const int nwords = H * wpr;
   const dim3 grid((nwords + kScanWordsPerBlock - 1) / kScanWordsPerBlock, B * K);
-  refine_scan_kernel<<<grid, kScanWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->hm_wmax, K, M, E, H, W, wpr,
-                                                       ws);
-  count_launch();
-  if ((rc = check_launch("refine_scan_kernel"))) return rc;
+  for (int pass_id = 0; pass_id < 2; ++pass_id) {
+    refine_scan_kernel<<<grid, kScanWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->hm_wmax, buf->scores_k, pass_id,
+                                                         K, M, E, H, W, wpr, ws);
+    count_launch();
+    if ((rc = check_launch("refine_scan_kernel"))) return rc;
+  }
   const int total = B * K * M;
   refine_apply_kernel<<<(total + 255) / 256, 256, 0, st>>>(buf->agg_hm, total, K, M, E, H, W, buf->poses, ws);
   count_launch();
