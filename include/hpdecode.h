@@ -128,7 +128,7 @@ HPD_EXPORT int hpd_topk(const HpdParams* p, const HpdBuffers* buf, void* stream)
 HPD_EXPORT int hpd_group(const HpdParams* p, const HpdBuffers* buf, void* stream);
 
 /* (e) adjust + person score + refine: grouping.py:172-191, :276, :193-250.
- * Reads agg_hm, agg_tags, hm_wmax, idx_k; updates poses in place; writes person_scores. */
+ * Reads agg_hm, agg_tags, hm_wmax, idx_k, scores_k, n_person; updates poses in place; writes person_scores. */
 HPD_EXPORT int hpd_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* workspace, size_t workspace_bytes,
                       void* stream);
 

@@ -51,6 +51,7 @@ struct AggArgs {
   int LO_R, LO_C, HI_R, HI_C, TG_R, TG_C;
   int vec_ok;
   int tags_preflipped;
+  int in_vec_ok;   // inputs allow 16-byte loads (aligned bases, strides multiples of 4 elements)
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -464,6 +465,11 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
                       a.W == 2 * S.hw && a.th == S.lh && a.tw == S.lw && a.W % 32 == 0 && S.lh >= 2 && S.lw >= 2 &&
                       a.vec_ok;
     if (fast) {
+      {
+        auto ok = [](const float* q, long long sb, long long sc_) { return q == nullptr || ((uintptr_t)q % 16 == 0 && sb % 4 == 0 && sc_ % 4 == 0); };
+        a.in_vec_ok = S.lw % 4 == 0 && ok(S.lo, S.lo_sb, S.lo_sc) && ok(S.hi, S.hi_sb, S.hi_sc) && ok(S.lo_f, S.lof_sb, S.lof_sc) &&
+                      ok(S.hi_f, S.hif_sb, S.hif_sc) && ok(a.tag, a.tag_sb, a.tag_sc) && ok(a.tag_f, a.tagf_sb, a.tagf_sc);
+      }
       const int NW = a.W >= 512 ? 4 : (a.W >= 256 ? 2 : 1);
       const size_t smem = sizeof(float) * x2::smem_floats(NW, a.E);
       const dim3 grid((a.W + 128 * NW - 1) / (128 * NW), (a.H + x2::RB - 1) / x2::RB, a.B * a.K);

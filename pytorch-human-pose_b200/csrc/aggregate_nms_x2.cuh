@@ -28,11 +28,11 @@ constexpr int LR = RB / 4 + 4;         // quarter-res rows staged (hm_lo)
 constexpr int TR = RB / 4 + 2;         // quarter-res rows staged (tags)
 constexpr int NROWS = RB + 4;          // output rows walked (band + 2 halo rows on each side)
 
-__host__ __device__ inline int SC(int NW) { return 64 * NW + 6; }   // half-res cols: hx0-3 ..
-__host__ __device__ inline int LC(int NW) { return 32 * NW + 4; }   // quarter-res cols: lx0-2 ..
-__host__ __device__ inline int TC(int NW) { return 32 * NW + 2; }   // quarter-res cols: lx0-1 ..
+__host__ __device__ inline int SC(int NW) { return 64 * NW + 8; }   // half-res cols: hx0-4 .. (interior 16B aligned)
+__host__ __device__ inline int LC(int NW) { return 32 * NW + 8; }   // quarter-res cols: lx0-4 ..
+__host__ __device__ inline int TC(int NW) { return 32 * NW + 8; }   // quarter-res cols: lx0-4 ..
 __host__ __device__ inline size_t smem_floats(int NW, int E) {
-  return (size_t)SR * SC(NW) + (size_t)LR * LC(NW) + (size_t)E * TR * TC(NW) + (size_t)NW * NROWS * 4 + 4 * SR + 4;
+  return (size_t)SR * SC(NW) + (size_t)LR * LC(NW) + (size_t)E * TR * TC(NW) + (size_t)NW * NROWS * 4 + 4 * SR + 8;
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -48,42 +48,116 @@ __device__ __forceinline__ void tap_x2(int o, int I, int& i0, int& i1, float& w0
 }
 
 // Stage a ROWS x COLS tile (origin (yo, xo), coordinates clamped to the map = border replication)
-// into shared memory.  One warp per tile row (lanes along x: coalesced), two rows per batch so that
-// 2 * ceil(COLS/32) independent loads per operand are in flight before the first one is consumed.
+// into shared memory.  COLS = 4 halo + interior + 4 halo columns, the interior starting at a
+// 16-byte aligned column of the map.  One warp per tile row, two rows per batch (all loads of a
+// batch are in flight before the first is consumed).  VEC: 16-byte loads/stores for the interior
+// (the flipped operand is read as the mirrored 16 bytes and reversed in registers), scalars for the
+// 8 halo columns and for any part right of the map.
 //   MODE 0: dst = p[y][x]      MODE 1: dst = pf[y][mirror ? w-1-x : x]
 //   MODE 2: dst = (p[y][x] + pf[y][w-1-x]) * 0.5   (flip averaging, model.py:90)
-template <int MODE, int ROWS, int COLS, int NW>
+template <int MODE>
+__device__ __forceinline__ float stage_combine(float v, float f) {
+  return (MODE == 2) ? __fmul_rn(__fadd_rn(v, f), 0.5f) : (MODE == 0 ? v : f);
+}
+
+template <int MODE, int ROWS, int COLS, int NW, bool VEC>
 __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float* __restrict__ p,
                                            const float* __restrict__ pf, bool mirror, int yo, int xo, int h, int w,
                                            int warp, int lane) {
-  constexpr int NIT = (COLS + 31) / 32, RPB = 2;
+  constexpr int RPB = 2;
   const int xm = w - 1;
+  const bool mir = (MODE == 2) || mirror;
+  if (VEC) {
+    constexpr int NV = (COLS - 8) / 4, VIT = (NV + 31) / 32;
 #pragma unroll 1
-  for (int r0 = warp * RPB; r0 < ROWS; r0 += NW * RPB) {
-    float v[RPB][NIT], f[RPB][NIT];
+    for (int r0 = warp * RPB; r0 < ROWS; r0 += NW * RPB) {
+      float4 v[RPB][VIT], f[RPB][VIT];
+      float hv[RPB], hf[RPB];
 #pragma unroll
-    for (int j = 0; j < RPB; ++j) {
-      const int r = r0 + j;
-      const size_t row = (size_t)clampi(yo + r, 0, h - 1) * w;
+      for (int j = 0; j < RPB; ++j) {
+        const int r = r0 + j;
+        const int row = clampi(yo + r, 0, h - 1) * w;
 #pragma unroll
-      for (int u = 0; u < NIT; ++u) {
-        const int c = lane + 32 * u;
-        v[j][u] = 0.f; f[j][u] = 0.f;
-        if (r < ROWS && c < COLS) {
+        for (int u = 0; u < VIT; ++u) {
+          const int q = lane + 32 * u;
+          const int x = xo + 4 + 4 * q;
+          v[j][u] = make_float4(0.f, 0.f, 0.f, 0.f);
+          f[j][u] = v[j][u];
+          if (r < ROWS && q < NV) {
+            if (x + 3 <= xm) {
+              if (MODE != 1) v[j][u] = __ldg(reinterpret_cast<const float4*>(p + row + x));
+              if (MODE != 0) {
+                if (mir) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(pf + row + (xm - x - 3)));
+                  f[j][u] = make_float4(t.w, t.z, t.y, t.x);
+                } else {
+                  f[j][u] = __ldg(reinterpret_cast<const float4*>(pf + row + x));
+                }
+              }
+            } else {   // right of the map: replicate the last column
+              float tv[4], tf[4];
+#pragma unroll
+              for (int c = 0; c < 4; ++c) {
+                const int xc = min(x + c, xm);
+                tv[c] = (MODE != 1) ? __ldg(p + row + xc) : 0.f;
+                tf[c] = (MODE != 0) ? __ldg(pf + row + (mir ? xm - xc : xc)) : 0.f;
+              }
+              v[j][u] = make_float4(tv[0], tv[1], tv[2], tv[3]);
+              f[j][u] = make_float4(tf[0], tf[1], tf[2], tf[3]);
+            }
+          }
+        }
+        hv[j] = 0.f; hf[j] = 0.f;
+        if (r < ROWS && lane < 8) {
+          const int c = (lane < 4) ? lane : COLS - 8 + lane;
           const int x = clampi(xo + c, 0, xm);
-          if (MODE != 1) v[j][u] = __ldg(p + row + x);
-          if (MODE != 0) f[j][u] = __ldg(pf + row + ((MODE == 2 || mirror) ? xm - x : x));
+          if (MODE != 1) hv[j] = __ldg(p + row + x);
+          if (MODE != 0) hf[j] = __ldg(pf + row + (mir ? xm - x : x));
         }
       }
+#pragma unroll
+      for (int j = 0; j < RPB; ++j) {
+        const int r = r0 + j;
+        if (r >= ROWS) break;
+#pragma unroll
+        for (int u = 0; u < VIT; ++u) {
+          const int q = lane + 32 * u;
+          if (q < NV)
+            *reinterpret_cast<float4*>(dst + r * COLS + 4 + 4 * q) =
+                make_float4(stage_combine<MODE>(v[j][u].x, f[j][u].x), stage_combine<MODE>(v[j][u].y, f[j][u].y),
+                            stage_combine<MODE>(v[j][u].z, f[j][u].z), stage_combine<MODE>(v[j][u].w, f[j][u].w));
+        }
+        if (lane < 8) dst[r * COLS + ((lane < 4) ? lane : COLS - 8 + lane)] = stage_combine<MODE>(hv[j], hf[j]);
+      }
     }
+  } else {
+    constexpr int NIT = (COLS + 31) / 32;
+#pragma unroll 1
+    for (int r0 = warp * RPB; r0 < ROWS; r0 += NW * RPB) {
+      float v[RPB][NIT], f[RPB][NIT];
 #pragma unroll
-    for (int j = 0; j < RPB; ++j) {
-      const int r = r0 + j;
+      for (int j = 0; j < RPB; ++j) {
+        const int r = r0 + j;
+        const int row = clampi(yo + r, 0, h - 1) * w;
 #pragma unroll
-      for (int u = 0; u < NIT; ++u) {
-        const int c = lane + 32 * u;
-        if (r < ROWS && c < COLS)
-          dst[r * COLS + c] = (MODE == 2) ? __fmul_rn(__fadd_rn(v[j][u], f[j][u]), 0.5f) : (MODE == 0 ? v[j][u] : f[j][u]);
+        for (int u = 0; u < NIT; ++u) {
+          const int c = lane + 32 * u;
+          v[j][u] = 0.f; f[j][u] = 0.f;
+          if (r < ROWS && c < COLS) {
+            const int x = clampi(xo + c, 0, xm);
+            if (MODE != 1) v[j][u] = __ldg(p + row + x);
+            if (MODE != 0) f[j][u] = __ldg(pf + row + (mir ? xm - x : x));
+          }
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < RPB; ++j) {
+        const int r = r0 + j;
+#pragma unroll
+        for (int u = 0; u < NIT; ++u) {
+          const int c = lane + 32 * u;
+          if (r < ROWS && c < COLS) dst[r * COLS + c] = stage_combine<MODE>(v[j][u], f[j][u]);
+        }
       }
     }
   }
@@ -92,7 +166,7 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float*
 template <int E, int NW>
 __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   extern __shared__ __align__(16) float smem[];
-  constexpr int sc = 64 * NW + 6, lc = 32 * NW + 4, tc = 32 * NW + 2;
+  constexpr int sc = 64 * NW + 8, lc = 32 * NW + 8, tc = 32 * NW + 8;
   float* sS = smem;                              // [SR][sc]   hi average, then stage mean S
   float* sL = sS + SR * sc;                      // [LR][lc]   flip-averaged hm_lo
   float* sT = sL + LR * lc;                      // [E][TR][tc] tags
@@ -101,7 +175,7 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   int* sRowI1 = sRowI0 + SR;
   float* sRowW0 = (float*)(sRowI1 + SR);
   float* sRowW1 = sRowW0 + SR;
-  float* sNegInf = sRowW1 + SR;                  // [4] dummy row for lanes right of the image
+  float* sNegInf = sRowW1 + SR;                  // [8] dummy row for lanes right of the image
 
   const ScaleDev& S = a.sc[0];
   const int tid = threadIdx.x;
@@ -110,29 +184,35 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   const int bk = blockIdx.z, b = bk / a.K, k = bk % a.K, kf = a.flip[k];
   const int H = a.H, W = a.W;
   const int x0 = blockIdx.x * 128 * NW, y0 = blockIdx.y * RB;
-  const int hxo = x0 / 2 - 3, hyo = y0 / 2 - 2;     // origins of the half-res tile
-  const int lxo = x0 / 4 - 2, lyo = y0 / 4 - 2;     // origins of the quarter-res hm tile
-  const int txo = x0 / 4 - 1, tyo = y0 / 4 - 1;     // origins of the tag tiles
+  const int hxo = x0 / 2 - 4, hyo = y0 / 2 - 2;     // origins of the half-res tile
+  const int lxo = x0 / 4 - 4, lyo = y0 / 4 - 2;     // origins of the quarter-res hm tile
+  const int txo = x0 / 4 - 4, tyo = y0 / 4 - 1;     // origins of the tag tiles
 
   // ---------------- phase 1: stage inputs ----------------------------------------------------------
   {
     const float* lo = S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc;
     const float* hi = S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc;
-    if (S.lo_f) {
-      stage_tile<2, LR, lc, NW>(sL, lo, S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc, true, lyo, lxo, S.lh, S.lw, warp, lane);
-      stage_tile<2, SR, sc, NW>(sS, hi, S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc, true, hyo, hxo, S.hh, S.hw, warp, lane);
-    } else {
-      stage_tile<0, LR, lc, NW>(sL, lo, nullptr, false, lyo, lxo, S.lh, S.lw, warp, lane);
-      stage_tile<0, SR, sc, NW>(sS, hi, nullptr, false, hyo, hxo, S.hh, S.hw, warp, lane);
-    }
-    stage_tile<0, TR, tc, NW>(sT, a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc, nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
-    if (E > 1) {
-      const bool unflip = !a.tags_preflipped;   // model.py:93: flip(tag_f, W)[:, FLIP]
-      stage_tile<1, TR, tc, NW>(sT + TR * tc, nullptr, a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc,
-                                unflip, tyo, txo, a.th, a.tw, warp, lane);
-    }
+    const float* lof = S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr;
+    const float* hif = S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr;
+    const float* tg0 = a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc;
+    const bool unflip = !a.tags_preflipped;   // model.py:93: flip(tag_f, W)[:, FLIP]
+    const float* tg1 = (E > 1) ? a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc : nullptr;
+#define HPD_STAGE_ALL(VEC_)                                                                                    \
+  do {                                                                                                         \
+    if (lof) {                                                                                                 \
+      stage_tile<2, LR, lc, NW, VEC_>(sL, lo, lof, true, lyo, lxo, S.lh, S.lw, warp, lane);                    \
+      stage_tile<2, SR, sc, NW, VEC_>(sS, hi, hif, true, hyo, hxo, S.hh, S.hw, warp, lane);                    \
+    } else {                                                                                                   \
+      stage_tile<0, LR, lc, NW, VEC_>(sL, lo, nullptr, false, lyo, lxo, S.lh, S.lw, warp, lane);               \
+      stage_tile<0, SR, sc, NW, VEC_>(sS, hi, nullptr, false, hyo, hxo, S.hh, S.hw, warp, lane);               \
+    }                                                                                                          \
+    stage_tile<0, TR, tc, NW, VEC_>(sT, tg0, nullptr, false, tyo, txo, a.th, a.tw, warp, lane);                \
+    if (E > 1) stage_tile<1, TR, tc, NW, VEC_>(sT + TR * tc, nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane); \
+  } while (0)
+    if (a.in_vec_ok) HPD_STAGE_ALL(true); else HPD_STAGE_ALL(false);
+#undef HPD_STAGE_ALL
   }
-  if (tid < 4) sNegInf[tid] = -INFINITY;
+  if (tid < 8) sNegInf[tid] = -INFINITY;
   if (tid < SR) {   // vertical taps of phase 2: half-res row -> rows of sL
     int i0, i1; float w0, w1;
     tap_x2(clampi(hyo + tid, 0, S.hh - 1), S.lh, i0, i1, w0, w1);
@@ -159,29 +239,32 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   const int xw = x0 + 128 * warp;                 // first column of this warp's strip
   const int ys = y0 - 2;                          // first walked row (even)
   float* edge = sEdge + warp * NROWS * 4;
-  if (lane < 4) {
-    const int xe = (lane < 2) ? xw - 2 + lane : xw + 126 + lane;   // xw-2, xw-1, xw+128, xw+129
-    const bool in_img = xe >= 0 && xe < W;
-    // xe >= 126 whenever it is inside the image, so no first-column special case here
-    const int h = xe >> 1;
-    const int ca = ((xe & 1) ? h : h - 1) - hxo, cb = ca + 1;
-    const float wa = (xe & 1) ? 0.75f : 0.25f, wb = (xe & 1) ? 0.25f : 0.75f;
-    float hA = 0.f, hB = 0.f, hC;
-    if (in_img) {
-      hA = fmaf(wa, sS[0 * sc + ca], __fmul_rn(wb, sS[0 * sc + cb]));
-      hB = fmaf(wa, sS[1 * sc + ca], __fmul_rn(wb, sS[1 * sc + cb]));
-    }
-    for (int p = 0; p < NROWS / 2; ++p) {
-      const int ye = ys + 2 * p;
-      float ve = -INFINITY, vo = -INFINITY;
-      if (in_img) {
-        hC = fmaf(wa, sS[(p + 2) * sc + ca], __fmul_rn(wb, sS[(p + 2) * sc + cb]));
-        if (ye >= 0 && ye < H) ve = (ye == 0) ? fmaf(1.f, hB, __fmul_rn(0.f, hC)) : fmaf(0.25f, hA, __fmul_rn(0.75f, hB));
-        if (ye + 1 >= 0 && ye + 1 < H) vo = fmaf(0.75f, hB, __fmul_rn(0.25f, hC));
-        hA = hB; hB = hC;
+  // 4 columns x NROWS rows = 144 independent values, spread over all 32 lanes (value i = lane + 32u:
+  // row t = i / 4, column e = i % 4); each is the same two-step lerp the walk performs.
+#pragma unroll
+  for (int u = 0; u < (NROWS * 4 + 31) / 32; ++u) {
+    const int i = lane + 32 * u;
+    if (i < NROWS * 4) {
+      const int t = i >> 2, e = i & 3;
+      const int xe = (e < 2) ? xw - 2 + e : xw + 126 + e;            // xw-2, xw-1, xw+128, xw+129
+      const int y = ys + t;
+      float v = -INFINITY;
+      if (xe >= 0 && xe < W && y >= 0 && y < H) {
+        // xe >= 126 whenever it is inside the image, so no first-column special case here
+        const int h = xe >> 1;
+        const int ca = ((xe & 1) ? h : h - 1) - hxo;
+        const float wa = (xe & 1) ? 0.75f : 0.25f, wb = (xe & 1) ? 0.25f : 0.75f;
+        // rows of the half-res tile: even y = 2j -> (j-1, j) = (t/2, t/2+1); odd -> (j, j+1) = ((t-1)/2+1, +2);
+        // the first image row clamps to (row 0, row 1) with weights (1, 0)
+        const bool odd = t & 1, first = (y == 0);
+        const int ra = (odd || first) ? (t >> 1) + 1 : (t >> 1);
+        const float wya = first ? 1.f : (odd ? 0.75f : 0.25f), wyb = first ? 0.f : (odd ? 0.25f : 0.75f);
+        const float* s0 = sS + ra * sc + ca;
+        const float ha = fmaf(wa, s0[0], __fmul_rn(wb, s0[1]));
+        const float hb = fmaf(wa, s0[sc], __fmul_rn(wb, s0[sc + 1]));
+        v = fmaf(wya, ha, __fmul_rn(wyb, hb));
       }
-      edge[(2 * p) * 4 + lane] = ve;
-      edge[(2 * p + 1) * 4 + lane] = vo;
+      edge[i] = v;
     }
   }
   __syncwarp();
@@ -196,11 +279,13 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
     const float wa0 = x_first ? 1.f : 0.25f, wb0 = x_first ? 0.f : 0.75f;
     const float NINF = -INFINITY;
     // lanes right of the image read a dummy row of -inf (stride 0), which makes all their values -inf
-    const float* srow = active ? (sS + 64 * warp + 2 * lane + 2) : sNegInf;
+    const float* srow = active ? (sS + 64 * warp + 2 * lane + 3) : sNegInf + 1;   // &S[h0-1]
     const int sstride = active ? sc : 0;
     auto hpass = [&](int r, float (&h)[4]) {
-      const float2 p = *reinterpret_cast<const float2*>(srow + r * sstride);
-      const float2 q = *reinterpret_cast<const float2*>(srow + r * sstride + 2);
+      const float* sp = srow + r * sstride;
+      const float2 mid = *reinterpret_cast<const float2*>(sp + 1);      // S[h0], S[h0+1] (8-byte aligned)
+      const float2 p = make_float2(sp[0], mid.x);
+      const float2 q = make_float2(mid.y, sp[3]);
       const float a0 = x_first ? p.y : p.x, b0 = x_first ? q.x : p.y;
       h[0] = fmaf(wa0, a0, __fmul_rn(wb0, b0));
       h[1] = fmaf(0.75f, p.y, __fmul_rn(0.25f, q.x));
