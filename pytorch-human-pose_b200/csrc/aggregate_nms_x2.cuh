@@ -221,16 +221,35 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   __syncthreads();
 
   // ---------------- phase 2: S = (up2(lo) + hi) * 0.5 in place (results.py:225-226) -------------
+  // Bands that touch neither the first nor the last rows of the image need no clamping, so the row
+  // taps are compile-time: the quarter-res rows are interpolated horizontally once per column
+  // (registers) and combined vertically; the two border bands take the table-driven path.
+  const bool interior_band = (y0 >= RB) && (y0 + 2 * RB <= H);
   for (int c = tid; c < sc; c += nthr) {
     int c0, c1; float wx0, wx1;
     tap_x2(clampi(hxo + c, 0, S.hw - 1), S.lw, c0, c1, wx0, wx1);
     c0 -= lxo; c1 -= lxo;
+    if (interior_band) {
+      float hq[LR];
+#pragma unroll
+      for (int i = 0; i < LR; ++i) hq[i] = fmaf(wx0, sL[i * lc + c0], __fmul_rn(wx1, sL[i * lc + c1]));
+#pragma unroll
+      for (int r = 0; r < SR; ++r) {
+        // half-res row hyo + r (hyo even): even -> quarter rows (k-1, k) = tile rows (r/2, r/2+1), weights (.25,.75);
+        // odd -> (k, k+1) = tile rows ((r-1)/2+1, (r-1)/2+2), weights (.75,.25)
+        const int i0 = (r & 1) ? (r >> 1) + 1 : (r >> 1);
+        const float up = (r & 1) ? fmaf(0.75f, hq[i0], __fmul_rn(0.25f, hq[i0 + 1]))
+                                 : fmaf(0.25f, hq[i0], __fmul_rn(0.75f, hq[i0 + 1]));
+        sS[r * sc + c] = __fmul_rn(__fadd_rn(up, sS[r * sc + c]), 0.5f);
+      }
+    } else {
 #pragma unroll 4
-    for (int r = 0; r < SR; ++r) {
-      const float* r0 = sL + sRowI0[r] * lc;
-      const float* r1 = sL + sRowI1[r] * lc;
-      const float up = lerp2(wx0, wx1, sRowW0[r], sRowW1[r], r0[c0], r0[c1], r1[c0], r1[c1]);
-      sS[r * sc + c] = __fmul_rn(__fadd_rn(up, sS[r * sc + c]), 0.5f);
+      for (int r = 0; r < SR; ++r) {
+        const float* r0 = sL + sRowI0[r] * lc;
+        const float* r1 = sL + sRowI1[r] * lc;
+        const float up = lerp2(wx0, wx1, sRowW0[r], sRowW1[r], r0[c0], r0[c1], r1[c0], r1[c1]);
+        sS[r * sc + c] = __fmul_rn(__fadd_rn(up, sS[r * sc + c]), 0.5f);
+      }
     }
   }
   __syncthreads();

@@ -236,28 +236,31 @@ __global__ void __launch_bounds__(32) group_kernel(const float* __restrict__ sco
       mean0 = mv[0];
       mean1 = (E > 1) ? mv[1] : 0.f;
     }
-    // cost matrix rows (grouping.py:116-128); rows >= nr are munkres' zero padding
-    for (int p = 0; p < n; ++p) {
-      const float m0 = __shfl_sync(kFull, mean0, p), m1 = __shfl_sync(kFull, mean1, p);
-      if (lane < n) {
-        double c;
-        if (lane >= nr) {
-          c = 0.0;
-        } else if (p < G) {
-          const double d0 = __dsub_rn((double)a_t0, (double)m0);
+    // cost matrix (grouping.py:116-128), one (detection, person) pair per lane and step
+    {
+      const int npairs = nr * G;
+      const unsigned inv = (65536u + G - 1) / G;         // i / G == (i * inv) >> 16 for i < 2048
+      for (int i = lane; i < ((npairs + 31) & ~31); i += 32) {
+        const int a = min((int)(((unsigned)i * inv) >> 16), nr - 1);
+        const int p = (i < npairs) ? i - a * G : 0;
+        const float t0 = __shfl_sync(kFull, a_t0, a), t1 = __shfl_sync(kFull, a_t1, a);
+        const float sc_a = __shfl_sync(kFull, a_score, a);
+        const float m0 = __shfl_sync(kFull, mean0, p), m1 = __shfl_sync(kFull, mean1, p);
+        if (i < npairs) {
+          const double d0 = __dsub_rn((double)t0, (double)m0);
           double s = __dmul_rn(d0, d0);
           if (E > 1) {
-            const double d1 = __dsub_rn((double)a_t1, (double)m1);
+            const double d1 = __dsub_rn((double)t1, (double)m1);
             s = __dadd_rn(s, __dmul_rn(d1, d1));
           }
           const double dn = __dsqrt_rn(s);
-          sm.D[lane][p] = dn;
-          c = __dsub_rn(__dmul_rn(rint(dn), 100.0), (double)a_score);
-        } else {
-          c = 1e10;
+          sm.D[a][p] = dn;
+          sm.C[a][p] = __dsub_rn(__dmul_rn(rint(dn), 100.0), (double)sc_a);
         }
-        sm.C[lane][p] = c;
       }
+      // more detections than persons: 1e10 columns (grouping.py:126-128); fewer: munkres pads zero rows
+      if (lane < nr) for (int p = G; p < n; ++p) sm.C[lane][p] = 1e10;
+      if (lane < n) for (int a = nr; a < n; ++a) sm.C[a][lane] = 0.0;
     }
     __syncwarp();
     const int star = munkres_warp(sm.C, n, lane);
