@@ -32,7 +32,8 @@ __host__ __device__ inline int SC(int NW) { return 64 * NW + 8; }   // half-res 
 __host__ __device__ inline int LC(int NW) { return 32 * NW + 8; }   // quarter-res cols: lx0-4 ..
 __host__ __device__ inline int TC(int NW) { return 32 * NW + 8; }   // quarter-res cols: lx0-4 ..
 __host__ __device__ inline size_t smem_floats(int NW, int E) {
-  return (size_t)SR * SC(NW) + (size_t)LR * LC(NW) + (size_t)E * TR * TC(NW) + (size_t)NW * NROWS * 4 + 4 * SR + 8;
+  (void)E;   // the tag tiles (E * TR * TC <= SR * SC floats) alias the half-res tile
+  return (size_t)SR * SC(NW) + (size_t)LR * LC(NW) + (size_t)NW * NROWS * 4 + 4 * SR + 8;
 }
 
 __device__ __forceinline__ int clampi(int v, int lo, int hi) { return v < lo ? lo : (v > hi ? hi : v); }
@@ -169,8 +170,8 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   constexpr int sc = 64 * NW + 8, lc = 32 * NW + 8, tc = 32 * NW + 8;
   float* sS = smem;                              // [SR][sc]   hi average, then stage mean S
   float* sL = sS + SR * sc;                      // [LR][lc]   flip-averaged hm_lo
-  float* sT = sL + LR * lc;                      // [E][TR][tc] tags
-  float* sEdge = sT + E * TR * tc;               // [NW][NROWS][4] halo-column values per warp
+  float* sT = smem;                              // [E][TR][tc] tags -- aliases sS, consumed (phase 0) before sS is staged
+  float* sEdge = sL + LR * lc;                   // [NW][NROWS][4] halo-column values per warp
   int* sRowI0 = (int*)(sEdge + NW * NROWS * 4);  // [SR] phase-2 vertical taps (rows of sL)
   int* sRowI1 = sRowI0 + SR;
   float* sRowW0 = (float*)(sRowI1 + SR);
@@ -188,15 +189,99 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   const int lxo = x0 / 4 - 4, lyo = y0 / 4 - 2;     // origins of the quarter-res hm tile
   const int txo = x0 / 4 - 4, tyo = y0 / 4 - 1;     // origins of the tag tiles
 
-  // ---------------- phase 1: stage inputs ----------------------------------------------------------
+  const int xw = x0 + 128 * warp;                 // first column of this warp's strip
+  const int X0 = xw + 4 * lane;                   // this lane's 4 output columns
+  const bool active = X0 < W;
+
+  // ---------------- phase 0a: stage the tag tiles (they alias the half-res tile) ---------------------
+  {
+    const float* tg0 = a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc;
+    const bool unflip = !a.tags_preflipped;   // model.py:93: flip(tag_f, W)[:, FLIP]
+    const float* tg1 = (E > 1) ? a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc : nullptr;
+    if (a.in_vec_ok) {
+      stage_tile<0, TR, tc, NW, true>(sT, tg0, nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
+      if (E > 1) stage_tile<1, TR, tc, NW, true>(sT + TR * tc, nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane);
+    } else {
+      stage_tile<0, TR, tc, NW, false>(sT, tg0, nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
+      if (E > 1) stage_tile<1, TR, tc, NW, false>(sT + TR * tc, nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane);
+    }
+  }
+  __syncthreads();
+  // ---------------- phase 0b: tags, x4 taps (results.py:229-230) ------------------------------------
+  if (active) {
+    const int q = X0 >> 2;                       // this lane's quarter-res column
+    const int tb = q - 1 - txo;                  // index of T[q-1] in a tile row
+    const bool x_first = (q == 0);
+    // columns 4q+{0,1}: taps (q-1,q) weights (.375,.625),(.125,.875); 4q+{2,3}: (q,q+1) (.875,.125),(.625,.375)
+    const float wa0 = x_first ? 1.f : 0.375f, wb0 = x_first ? 0.f : 0.625f;
+    const float wa1 = x_first ? 1.f : 0.125f, wb1 = x_first ? 0.f : 0.875f;
+    float hA[E][4], hB[E][4];
+    auto hpass = [&](int r, float (&h)[E][4]) {
+#pragma unroll
+      for (int e = 0; e < E; ++e) {
+        const float* t = sT + e * TR * tc + r * tc + tb;
+        const float t0 = t[0], t1 = t[1], t2 = t[2];
+        const float a0 = x_first ? t1 : t0, b0 = x_first ? t2 : t1;
+        h[e][0] = fmaf(wa0, a0, __fmul_rn(wb0, b0));
+        h[e][1] = fmaf(wa1, a0, __fmul_rn(wb1, b0));
+        h[e][2] = fmaf(0.875f, t1, __fmul_rn(0.125f, t2));
+        h[e][3] = fmaf(0.625f, t1, __fmul_rn(0.375f, t2));
+      }
+    };
+    float* tg_plane = a.agg_tags + ((size_t)b * a.K + k) * H * W * E;
+    auto emit = [&](int y, float wy0, float wy1, const float (&A)[E][4], const float (&Bv)[E][4]) {
+      if (y < y0 || y >= y0 + RB || y >= H) return;
+      float o[E][4];
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) o[e][c] = fmaf(wy0, A[e][c], __fmul_rn(wy1, Bv[e][c]));
+      float* dst = tg_plane + ((size_t)y * W + X0) * E;
+      if (E == 1) {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+      } else {
+        *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[E - 1][0], o[0][1], o[E - 1][1]);
+        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[0][2], o[E - 1][2], o[0][3], o[E - 1][3]);
+      }
+    };
+    // tile rows: r <-> quarter-res row tyo + r = y0/4 - 1 + r.  Rows y0, y0+1 use (i-1, i) with
+    // i = y0/4, i.e. tile rows (0, 1); then each group of 4 rows 4i+2..4i+5 uses rows (i, i+1).
+    hpass(0, hA);
+    hpass(1, hB);
+    if (y0 == 0) {          // first two rows of the image: src clamps to 0 -> taps (row 0, row 1), weights (1, 0)
+      float hC[E][4];
+      hpass(2, hC);         // tile row 1 = image row 0, tile row 2 = image row 1
+      emit(0, 1.f, 0.f, hB, hC);
+      emit(1, 1.f, 0.f, hB, hC);
+    } else {
+      emit(y0, 0.375f, 0.625f, hA, hB);
+      emit(y0 + 1, 0.125f, 0.875f, hA, hB);
+    }
+#pragma unroll 1
+    for (int g = 0; g < RB / 4; ++g) {
+      // rows y0 + 4g + 2 .. y0 + 4g + 5 : taps (tile row g+1, tile row g+2)
+#pragma unroll
+      for (int e = 0; e < E; ++e)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) hA[e][c] = hB[e][c];
+      hpass(g + 2, hB);
+      const int y = y0 + 4 * g + 2;
+      emit(y, 0.875f, 0.125f, hA, hB);
+      emit(y + 1, 0.625f, 0.375f, hA, hB);
+      if (g + 1 < RB / 4) {
+        emit(y + 2, 0.375f, 0.625f, hA, hB);
+        emit(y + 3, 0.125f, 0.875f, hA, hB);
+      }
+    }
+  }
+  __syncthreads();   // every warp is done with the tag tiles before the half-res tile overwrites them
+
+  // ---------------- phase 1: stage the heatmap inputs -------------------------------------------------
   {
     const float* lo = S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc;
     const float* hi = S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc;
     const float* lof = S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr;
     const float* hif = S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr;
-    const float* tg0 = a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc;
-    const bool unflip = !a.tags_preflipped;   // model.py:93: flip(tag_f, W)[:, FLIP]
-    const float* tg1 = (E > 1) ? a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc : nullptr;
 #define HPD_STAGE_ALL(VEC_)                                                                                    \
   do {                                                                                                         \
     if (lof) {                                                                                                 \
@@ -206,8 +291,6 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
       stage_tile<0, LR, lc, NW, VEC_>(sL, lo, nullptr, false, lyo, lxo, S.lh, S.lw, warp, lane);               \
       stage_tile<0, SR, sc, NW, VEC_>(sS, hi, nullptr, false, hyo, hxo, S.hh, S.hw, warp, lane);               \
     }                                                                                                          \
-    stage_tile<0, TR, tc, NW, VEC_>(sT, tg0, nullptr, false, tyo, txo, a.th, a.tw, warp, lane);                \
-    if (E > 1) stage_tile<1, TR, tc, NW, VEC_>(sT + TR * tc, nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane); \
   } while (0)
     if (a.in_vec_ok) HPD_STAGE_ALL(true); else HPD_STAGE_ALL(false);
 #undef HPD_STAGE_ALL
@@ -255,7 +338,6 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   __syncthreads();
 
   // ---------------- phase 3a: per-warp prologue, values of the 4 halo columns ------------------
-  const int xw = x0 + 128 * warp;                 // first column of this warp's strip
   const int ys = y0 - 2;                          // first walked row (even)
   float* edge = sEdge + warp * NROWS * 4;
   // 4 columns x NROWS rows = 144 independent values, spread over all 32 lanes (value i = lane + 32u:
@@ -291,8 +373,6 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   // ---------------- phase 3b: walk the rows, 4 columns per lane ------------------------------------
   // Four rows per loop iteration so that the register windows (4 row-maxima rows, 2 value rows,
   // 2 interpolated half-res rows) rotate by renaming instead of by moves.
-  const int X0 = xw + 4 * lane;
-  const bool active = X0 < W;
   {
     const bool x_first = (X0 == 0);
     const float wa0 = x_first ? 1.f : 0.25f, wb0 = x_first ? 0.f : 0.75f;
@@ -423,73 +503,6 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
     }
   }
 
-  // ---------------- phase 4: tags, x4 taps (results.py:229-230) -------------------------------------
-  if (active) {
-    const int q = X0 >> 2;                       // this lane's quarter-res column
-    const int tb = q - 1 - txo;                  // index of T[q-1] in a tile row
-    const bool x_first = (q == 0);
-    // columns 4q+{0,1}: taps (q-1,q) weights (.375,.625),(.125,.875); 4q+{2,3}: (q,q+1) (.875,.125),(.625,.375)
-    const float wa0 = x_first ? 1.f : 0.375f, wb0 = x_first ? 0.f : 0.625f;
-    const float wa1 = x_first ? 1.f : 0.125f, wb1 = x_first ? 0.f : 0.875f;
-    float hA[E][4], hB[E][4];
-    auto hpass = [&](int r, float (&h)[E][4]) {
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const float* t = sT + e * TR * tc + r * tc + tb;
-        const float t0 = t[0], t1 = t[1], t2 = t[2];
-        const float a0 = x_first ? t1 : t0, b0 = x_first ? t2 : t1;
-        h[e][0] = fmaf(wa0, a0, __fmul_rn(wb0, b0));
-        h[e][1] = fmaf(wa1, a0, __fmul_rn(wb1, b0));
-        h[e][2] = fmaf(0.875f, t1, __fmul_rn(0.125f, t2));
-        h[e][3] = fmaf(0.625f, t1, __fmul_rn(0.375f, t2));
-      }
-    };
-    float* tg_plane = a.agg_tags + ((size_t)b * a.K + k) * H * W * E;
-    auto emit = [&](int y, float wy0, float wy1, const float (&A)[E][4], const float (&Bv)[E][4]) {
-      if (y < y0 || y >= y0 + RB || y >= H) return;
-      float o[E][4];
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) o[e][c] = fmaf(wy0, A[e][c], __fmul_rn(wy1, Bv[e][c]));
-      float* dst = tg_plane + ((size_t)y * W + X0) * E;
-      if (E == 1) {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
-      } else {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[E - 1][0], o[0][1], o[E - 1][1]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[0][2], o[E - 1][2], o[0][3], o[E - 1][3]);
-      }
-    };
-    // tile rows: r <-> quarter-res row tyo + r = y0/4 - 1 + r.  Rows y0, y0+1 use (i-1, i) with
-    // i = y0/4, i.e. tile rows (0, 1); then each group of 4 rows 4i+2..4i+5 uses rows (i, i+1).
-    hpass(0, hA);
-    hpass(1, hB);
-    if (y0 == 0) {          // first two rows of the image: src clamps to 0 -> taps (row 0, row 1), weights (1, 0)
-      float hC[E][4];
-      hpass(2, hC);         // tile row 1 = image row 0, tile row 2 = image row 1
-      emit(0, 1.f, 0.f, hB, hC);
-      emit(1, 1.f, 0.f, hB, hC);
-    } else {
-      emit(y0, 0.375f, 0.625f, hA, hB);
-      emit(y0 + 1, 0.125f, 0.875f, hA, hB);
-    }
-#pragma unroll 1
-    for (int g = 0; g < RB / 4; ++g) {
-      // rows y0 + 4g + 2 .. y0 + 4g + 5 : taps (tile row g+1, tile row g+2)
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) hA[e][c] = hB[e][c];
-      hpass(g + 2, hB);
-      const int y = y0 + 4 * g + 2;
-      emit(y, 0.875f, 0.125f, hA, hB);
-      emit(y + 1, 0.625f, 0.375f, hA, hB);
-      if (g + 1 < RB / 4) {
-        emit(y + 2, 0.375f, 0.625f, hA, hB);
-        emit(y + 3, 0.125f, 0.875f, hA, hB);
-      }
-    }
-  }
 }
 
 }  // namespace x2
