@@ -201,31 +201,22 @@ def run_ours(args):
     F = MAX_PEOPLE * K_JOINTS * 5 + MAX_PEOPLE + 2
     from hpdecode.decoder import DecodeResult
 
-    # One buffer set + CUDA stream per batch in flight: batch i+1's bandwidth-bound aggregation kernel
-    # overlaps batch i's latency-bound top-k / grouping / refine kernels (which occupy a few SMs each).
+    # DecodePipeline keeps NS batches in flight: batch i+1's bandwidth-bound aggregation kernel overlaps batch
+    # i's latency-bound top-k / grouping / refine kernels (high-priority streams, a few SMs each).
+    from hpdecode.decoder import DecodePipeline
     NS = max(1, args.streams)
-    lanes = []
-    for s_ in range(NS):
-        lanes.append({
-            "bufs": dec.buffers(B, S, S, 2, slot=s_),
-            "stream": torch.cuda.Stream(device=dev),
-            "gathered": torch.empty((world * B, F), device=dev) if (world > 1 and rank == 0) else None,
-            "staging": {k: torch.empty_like(v) for k, v in resident.items()},
-            "result_host": torch.empty((B, F), dtype=torch.float32).pin_memory(),
-        })
+    pipe = DecodePipeline(dec, depth=NS, split_priority=args.split_priority)
+    extra = [{"gathered": torch.empty((world * B, F), device=dev) if (world > 1 and rank == 0) else None,
+              "staging": {k: torch.empty_like(v) for k, v in resident.items()},
+              "result_host": torch.empty((B, F), dtype=torch.float32).pin_memory()} for _ in range(NS)]
     stages = ("aggregate_nms", "topk", "group", "adjust_refine")
     main = torch.cuda.current_stream(dev)
+    bufs = dec.buffers(B, S, S, 2, slot=0)
 
-    def step(ln, scales, events=None):
-        for i, st in enumerate(stages):
-            if events is not None:
-                events[i].record()
-            ops.run_stage(st, ln["bufs"], params, scales=scales)
-        if events is not None:
-            events[len(stages)].record()
-        packed = DecodeResult(ln["bufs"]).packed()
+    def finish(ln, res):
+        packed = res.packed()
         if world > 1:
-            gather_packed_equal(packed, ln["gathered"], dst=0)
+            gather_packed_equal(packed, extra[ln["slot"]]["gathered"], dst=0)
         return packed
 
     def barrier():
@@ -233,50 +224,57 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    def run_steps(n, fn):
-        """n steps round-robin over the lanes; returns device time (ms) from fork to join on the main stream."""
+    def run_steps(n, submit):
+        """n pipelined steps; returns device time (ms) from fork to join on the main stream."""
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
         t0.record(main)
-        for ln in lanes:
-            ln["stream"].wait_stream(main)
-        for i in range(n):
-            ln = lanes[i % NS]
-            with torch.cuda.stream(ln["stream"]):
-                fn(ln, i)
-        for ln in lanes:
-            main.wait_stream(ln["stream"])
+        for _ in range(n):
+            submit()
+        pipe.drain()
         t1.record(main)
         barrier()
         return t0.elapsed_time(t1)
 
+    def value_step():
+        pipe.submit([resident], (S, S), after_tail=finish)
+
     # ---- value: inputs resident in HBM -------------------------------------------------------------
-    run_steps(max(args.warmup, 3) * NS, lambda ln, i: step(ln, [resident]))
-    # the roofline kernel's own duration: K launches alone on the GPU, CUDA events on its stream
+    run_steps(max(args.warmup, 3) * NS, value_step)
+    # per-stage durations: K sequential steps, one batch in flight, CUDA events on the launching stream
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(args.steps)]
     for i in range(args.steps):
-        step(lanes[0], [resident], evs[i])
+        for j, st in enumerate(stages):
+            evs[i][j].record()
+            ops.run_stage(st, bufs, params, scales=[resident])
+        evs[i][len(stages)].record()
     barrier()
     stage_ms = [statistics.mean(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(args.steps)) for j in range(len(stages))]
     seq_ms = evs[0][0].elapsed_time(evs[-1][len(stages)]) / args.steps
     sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.launches_total()
-    ms_total = run_steps(args.steps, lambda ln, i: step(ln, [resident]))
+    ms_total = run_steps(args.steps, value_step)
     launches = ops.launches_total() - l0
 
     # ---- e2e: host buffers, H2D of the inputs and D2H of the pose lists inside the timed region ---------
-    def e2e_step(ln, i):
-        for k in ln["staging"]:
-            ln["staging"][k].copy_(pinned[k], non_blocking=True)
-        packed = step(ln, [ln["staging"]])
-        src = ln["gathered"] if (world > 1 and rank == 0) else packed
-        ln["result_host"].copy_(src[:B], non_blocking=True)
+    def e2e_step():
+        def h2d(ln):
+            st = extra[ln["slot"]]["staging"]
+            for k in st:
+                st[k].copy_(pinned[k], non_blocking=True)
+            return [st]
+
+        def d2h(ln, res):
+            packed = finish(ln, res)
+            src = extra[ln["slot"]]["gathered"] if (world > 1 and rank == 0) else packed
+            extra[ln["slot"]]["result_host"].copy_(src[:B], non_blocking=True)
+
+        pipe.submit([resident], (S, S), before_agg=h2d, after_tail=d2h)
 
     run_steps(2 * NS, e2e_step)
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms = run_steps(e2e_steps, e2e_step)
     clocks = sampler.stop() if sampler else None
-    bufs = lanes[0]["bufs"]
 
     # max over ranks
     if world > 1:
@@ -337,7 +335,8 @@ def main():
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--streams", type=int, default=3, help="batches in flight per GPU (1 = strictly sequential)")
+    ap.add_argument("--split-priority", action="store_true")
+    ap.add_argument("--streams", type=int, default=4, help="batches in flight per GPU (1 = strictly sequential)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

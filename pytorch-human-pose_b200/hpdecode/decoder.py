@@ -104,3 +104,72 @@ class BottomUpDecoder:
                                  self.refine)
         ops.run_decode(None, bufs, params)
         return DecodeResult(bufs)
+
+
+class DecodePipeline:
+    """Keeps ``depth`` batches in flight on one GPU.
+
+    The path has one bandwidth-bound kernel (fused aggregation + NMS) followed by three latency-bound
+    ones (top-k, grouping, refine) that occupy a handful of SMs each.  Every lane owns a buffer set,
+    a normal-priority stream for the aggregation kernel and a high-priority stream for the rest, so
+    batch i+1's aggregation overlaps batch i's tail and the small kernels get SM slots as soon as
+    they are runnable.  ``submit`` returns the lane's DecodeResult; it stays valid until the lane is
+    reused ``depth`` submits later (call ``result.ready.synchronize()`` or ``drain()`` before reading).
+    """
+
+    def __init__(self, decoder: "BottomUpDecoder", depth: int = 3, split_priority: bool = False):
+        self.dec = decoder
+        self.depth = max(1, depth)
+        dev = decoder.device
+        self.lanes = []
+        for i in range(self.depth):
+            s_agg = torch.cuda.Stream(device=dev, priority=0)
+            # split_priority: the tail kernels run on their own high-priority stream (measured slightly
+            # slower on B200 than one stream per lane, so it is off by default)
+            s_tail = torch.cuda.Stream(device=dev, priority=-1) if split_priority else s_agg
+            self.lanes.append({"slot": i, "s_agg": s_agg, "s_tail": s_tail, "agg_done": torch.cuda.Event(),
+                               "ready": torch.cuda.Event(), "used": False})
+        self._next = 0
+
+    def submit(self, scales: Sequence[dict], out_hw: Tuple[int, int], tag_scale: int = 0, before_agg=None,
+               after_tail=None) -> DecodeResult:
+        """Enqueue one batch.  ``before_agg(lane)`` / ``after_tail(lane, result)`` run on the lane's streams
+        (e.g. the H2D copies of the inputs and the D2H copy of the packed poses)."""
+        ln = self.lanes[self._next]
+        self._next = (self._next + 1) % self.depth
+        H, W = out_hw
+        B = scales[0]["hm_lo"].shape[0]
+        E = 2 if scales[tag_scale].get("tag_f") is not None else 1
+        d = self.dec
+        bufs = d.buffers(B, H, W, E, slot=ln["slot"])
+        params = ops.make_params(B, d.num_kpts, H, W, E, d.max_num_people, d.det_thr, d.tag_thr, d.adjust, d.refine,
+                                 len(scales), tag_scale)
+        cur = torch.cuda.current_stream(d.device)
+        ln["s_agg"].wait_stream(cur)
+        with torch.cuda.stream(ln["s_agg"]):
+            if ln["used"]:
+                ln["s_agg"].wait_event(ln["ready"])     # the lane's previous batch has been consumed
+            if before_agg is not None:
+                scales = before_agg(ln) or scales
+            ops.run_stage("aggregate_nms", bufs, params, scales=scales)
+            if ln["s_tail"] is not ln["s_agg"]:
+                ln["agg_done"].record()
+        res = DecodeResult(bufs)
+        with torch.cuda.stream(ln["s_tail"]):
+            if ln["s_tail"] is not ln["s_agg"]:
+                ln["s_tail"].wait_event(ln["agg_done"])
+            for st in ("topk", "group", "adjust_refine"):
+                ops.run_stage(st, bufs, params)
+            if after_tail is not None:
+                after_tail(ln, res)
+            ln["ready"].record()
+        ln["used"] = True
+        res.ready = ln["ready"]
+        return res
+
+    def drain(self):
+        """Make the current stream wait for everything submitted so far."""
+        cur = torch.cuda.current_stream(self.dec.device)
+        for ln in self.lanes:
+            if ln["used"]:
+                cur.wait_event(ln["ready"])
