@@ -89,7 +89,14 @@ def run_reference(args):
     if rank != 0:
         return
     cores = min(host_cores(), 32)
-    inputs = make_inputs(min(8, args.batch), args.size, seed=1)
+    if args.inputs == "hrnet":
+        import torch
+        from hpdecode import synth_net
+        dev = "cuda:0" if torch.cuda.is_available() else "cpu"      # producing the inputs is not part of the timed path
+        r = synth_net.network_outputs(min(8, args.batch), args.size, flip=True, seed=1, C=32, device=dev, chunk=2)
+        inputs = {k: v.contiguous().cpu().numpy() for k, v in r.items()}
+    else:
+        inputs = make_inputs(min(8, args.batch), args.size, seed=1)
     pool = CpuPool(args.size, cores, inputs)
     sample = cores                                     # one image per core per step (~6 s of wall clock)
     for _ in range(args.warmup):
@@ -193,9 +200,17 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
 
     B, S = args.batch, args.size
-    host = make_inputs(B, S, seed=1 + rank)
-    pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
-    resident = {k: v.to(dev) for k, v in pinned.items()}
+    if args.inputs == "hrnet":
+        # BASELINE: heatmaps / tags "produced by random-init HigherHRNet weights on synthetic images"
+        from hpdecode import synth_net
+        resident = synth_net.network_outputs(B, S, flip=True, seed=1 + rank, C=32, device=dev)
+        torch.cuda.synchronize()
+        pinned = {k: v.contiguous().cpu().pin_memory() for k, v in resident.items()}
+        host = {k: v[: min(8, B)].numpy() for k, v in pinned.items()}
+    else:
+        host = make_inputs(B, S, seed=1 + rank)
+        pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
+        resident = {k: v.to(dev) for k, v in pinned.items()}
     dec = BottomUpDecoder(K_JOINTS, MAX_PEOPLE, DET_THR, TAG_THR, dev)
     params = ops.make_params(B, K_JOINTS, S, S, 2, MAX_PEOPLE, DET_THR, TAG_THR)
     F = MAX_PEOPLE * K_JOINTS * 5 + MAX_PEOPLE + 2
@@ -207,7 +222,7 @@ def run_ours(args):
     NS = max(1, args.streams)
     pipe = DecodePipeline(dec, depth=NS, split_priority=args.split_priority)
     extra = [{"gathered": torch.empty((world * B, F), device=dev) if (world > 1 and rank == 0) else None,
-              "staging": {k: torch.empty_like(v) for k, v in resident.items()},
+              "staging": {k: torch.empty(v.shape, device=dev, dtype=v.dtype) for k, v in resident.items()},
               "result_host": torch.empty((B, F), dtype=torch.float32).pin_memory()} for _ in range(NS)]
     stages = ("aggregate_nms", "topk", "group", "adjust_refine")
     main = torch.cuda.current_stream(dev)
@@ -298,7 +313,9 @@ def run_ours(args):
             "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": "images/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": "synthetic (seeded smooth random fields with default-init HigherHRNet value ranges; no dataset/checkpoint offline)",
+            "data": ("synthetic: outputs of a default-init HigherHRNet-W32 (stock PyTorch, hpdecode/synth_net.py) on seeded N(0,1) "
+                     "images, flipped forward included; no dataset/checkpoint offline") if args.inputs == "hrnet" else
+                    "synthetic (seeded smooth random fields with default-init HigherHRNet value ranges)",
             "config": workload_config(args),
             "roofline": {"bound": "hbm", "kernel": "agg_nms (fused aggregation + NMS)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
@@ -336,6 +353,8 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--split-priority", action="store_true")
+    ap.add_argument("--inputs", default="hrnet", choices=["hrnet", "netlike"],
+                    help="hrnet: outputs of a default-init HigherHRNet-W32 on seeded random images; netlike: CPU-generated fields")
     ap.add_argument("--streams", type=int, default=4, help="batches in flight per GPU (1 = strictly sequential)")
     args = ap.parse_args()
     if args.impl == "reference":

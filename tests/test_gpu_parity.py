@@ -74,3 +74,25 @@ def test_decode_matches_oracle(case, oracle):
         np.testing.assert_allclose(ps, ref["person_scores"], rtol=RTOL, atol=0, err_msg=f"{name}[{b}] person scores")
         assert np.array_equal(_bits(gj), _bits(ref["grouped_joints"])), f"{name}[{b}] grouped joints (bit-exact)"
         assert np.array_equal(_bits(ps), _bits(ref["person_scores"])), f"{name}[{b}] person scores (bit-exact)"
+
+
+@pytest.mark.parametrize("C,size,B", [(32, 512, 2), (48, 384, 1)])
+def test_decode_of_random_init_higherhrnet_outputs(C, size, B, oracle):
+    """BASELINE configs 0-2: heatmaps / tags produced by a default-init HigherHRNet on synthetic images (flip
+    test), decoded on the device and by the oracle from the SAME in-memory tensors (conv outputs are not
+    bit-reproducible across devices).  hm_lo / tag are strided channel-slice views."""
+    from hpdecode import BottomUpDecoder, synth_net
+    scale = synth_net.network_outputs(B, size, flip=True, seed=3, C=C, device="cuda:0", chunk=2)
+    assert B == 1 or not scale["hm_lo"].is_contiguous()
+    dec = BottomUpDecoder(17, 30, 0.05, 0.5, "cuda:0")
+    res = dec.decode([scale], (size, size))
+    out = res.to_numpy()
+    host = {k: v.contiguous().cpu().numpy() for k, v in scale.items()}
+    for b in range(B):
+        hm_o, tg_o = oracle.aggregate([{k: v[b] for k, v in host.items()}], (size, size))
+        assert np.array_equal(_bits(res.agg_hm[b].cpu().numpy()), _bits(hm_o))
+        assert np.array_equal(_bits(res.agg_tags[b].cpu().numpy()), _bits(tg_o))
+        ref = oracle.parse(hm_o, tg_o, 30, 0.05, 0.5)
+        assert np.array_equal(res.bufs.idx_k[b].cpu().numpy(), ref["idx_k"])
+        assert np.array_equal(_bits(out[b][0]), _bits(ref["grouped_joints"]))
+        assert np.array_equal(_bits(out[b][1]), _bits(ref["person_scores"]))
