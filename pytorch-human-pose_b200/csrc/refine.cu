@@ -216,9 +216,12 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
         if (E > 1) t1 = t[(size_t)idx * E + 1];
       }
       bool improved = false;
-      for (int q = 0; q < cnt; ++q) {
+      // only the pairs whose running best this word's maximum can still reach
+      uint32_t todo = __ballot_sync(kFull, lane < cnt && hw_o >= (unsigned)(best >> 32));
+      while (todo) {
+        const int q = __ffs(todo) - 1;
+        todo &= todo - 1;
         const unsigned long long bq = __shfl_sync(kFull, best, q);
-        if (hw_o < (unsigned)(bq >> 32)) continue;
         const float v = refine_value(pv, t0, t1, __shfl_sync(kFull, T0, q), __shfl_sync(kFull, T1, q), E);
         const unsigned vo = valid ? ordered_u32(v) : 0u;
         if (!__any_sync(kFull, vo >= (unsigned)(bq >> 32))) continue;
