@@ -136,7 +136,7 @@ class ClockSampler:
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
-                                       "--format=csv,noheader,nounits", "-lms", "100"], stdout=self.f,
+                                       "--format=csv,noheader,nounits", "-lms", "20"], stdout=self.f,
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
@@ -256,6 +256,8 @@ def run_ours(args):
 
     # ---- value: inputs resident in HBM -------------------------------------------------------------
     run_steps(max(args.warmup, 3) * NS, value_step)
+    sampler = ClockSampler(local) if rank == 0 else None
+    time.sleep(0.2 if rank == 0 else 0.0)     # let nvidia-smi attach before the timed work starts
     # per-stage durations: K sequential steps, one batch in flight, CUDA events on the launching stream
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(args.steps)]
     for i in range(args.steps):
@@ -266,7 +268,6 @@ def run_ours(args):
     barrier()
     stage_ms = [statistics.mean(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(args.steps)) for j in range(len(stages))]
     seq_ms = evs[0][0].elapsed_time(evs[-1][len(stages)]) / args.steps
-    sampler = ClockSampler(local) if rank == 0 else None
     l0 = ops.launches_total()
     ms_total = run_steps(args.steps, value_step)
     launches = ops.launches_total() - l0

@@ -96,3 +96,47 @@ def test_decode_of_random_init_higherhrnet_outputs(C, size, B, oracle):
         assert np.array_equal(res.bufs.idx_k[b].cpu().numpy(), ref["idx_k"])
         assert np.array_equal(_bits(out[b][0]), _bits(ref["grouped_joints"]))
         assert np.array_equal(_bits(out[b][1]), _bits(ref["person_scores"]))
+
+
+def test_multiscale_decode_matches_oracle(oracle):
+    """BASELINE config 3 end to end at a test size: scales 0.5/1.0/1.5 + flip, heatmaps averaged over scales,
+    tags from scale 1.0, then the normal decode."""
+    from hpdecode import BottomUpDecoder
+    size = 512
+    scales = synth.netlike(2, size, True, seed=71, scales=(0.5, 1.0, 1.5))
+    dec = BottomUpDecoder(17, 30, 0.05, 0.5, "cuda:0")
+    res = dec.decode(_dev(scales), (size, size), tag_scale=1)
+    out = res.to_numpy()
+    for b in range(2):
+        hm_o, tg_o = oracle.aggregate(synth.image_slice(scales, b), (size, size), tag_scale=1)
+        assert np.array_equal(_bits(res.agg_hm[b].cpu().numpy()), _bits(hm_o))
+        ref = oracle.parse(hm_o, tg_o, 30, 0.05, 0.5)
+        assert np.array_equal(res.bufs.idx_k[b].cpu().numpy(), ref["idx_k"])
+        assert np.array_equal(_bits(out[b][0]), _bits(ref["grouped_joints"]))
+        assert np.array_equal(_bits(out[b][1]), _bits(ref["person_scores"]))
+
+
+def test_pipeline_gives_the_same_results_as_sequential_decode():
+    """DecodePipeline (batches in flight on several streams, buffer sets re-used) vs plain decode()."""
+    from hpdecode import BottomUpDecoder
+    from hpdecode.decoder import DecodePipeline
+    dec = BottomUpDecoder(17, 30, 0.05, 0.5, "cuda:0")
+    batches = [_dev(synth.crowd(2, 256, persons=5 + 3 * i, flip=True, seed=80 + i)) for i in range(5)]
+    want = []
+    for s in batches:
+        r = dec.decode(s, (256, 256), slot=99)
+        want.append([(g.copy(), p.copy()) for g, p in r.to_numpy()])
+    pipe = DecodePipeline(dec, depth=2)
+    got = []
+    keep = []
+    for s in batches:
+        holder = {}
+        pipe.submit(s, (256, 256), after_tail=lambda ln, res, h=holder: h.update(packed=res.packed().clone()))
+        keep.append(holder)
+    pipe.drain()
+    torch.cuda.synchronize()
+    for h in keep:
+        got.append(type(r).unpack(h["packed"].cpu().numpy(), 30, 17, 2))
+    for w, g in zip(want, got):
+        for (wg, wp), (gg, gp) in zip(w, g):
+            assert np.array_equal(_bits(wg), _bits(gg)) and np.array_equal(_bits(wp), _bits(gp))
