@@ -23,6 +23,7 @@ namespace hpd {
 namespace {
 
 constexpr int kTopkWarps = 4;
+constexpr int kLogCap = 768;   // entering elements logged per row (typical: 100-300)
 
 struct HeapRef {
   float* v;
@@ -124,7 +125,13 @@ struct SortedSink {
   float top;      // smallest kept value
   float evicted;  // value of the last evicted element (evictions are non-decreasing)
   bool any_evicted;
+  // log of the entering elements, in order: the exact sink goes through the same VALUE history, so a
+  // replay only has to feed it this list instead of scanning the row again
+  float* log_v;
+  int* log_i;
+  int n_log;
   __device__ __forceinline__ void init(float nv) {
+    n_log = 0;
     sv = lane < M ? nv : -INFINITY;
     si = lane;
     // bitonic sort, descending by value
@@ -150,6 +157,8 @@ struct SortedSink {
     const int ui = __shfl_up_sync(kFull, si, 1);
     evicted = top;
     any_evicted = true;
+    if (lane == 0 && n_log < kLogCap) { log_v[n_log] = cv; log_i[n_log] = idx; }
+    ++n_log;
     if (lane < M) {
       if (lane > pos) { sv = uv; si = ui; }
       else if (lane == pos) { sv = cv; si = idx; }
@@ -181,20 +190,25 @@ __device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ h
     sink.init(nv);
   }
   const int nwords = H * wpr;
-  constexpr int kGroup = 4, kSlots = 8;
-  float nxt[kGroup];
+  constexpr int kGroup = 4, kSlots = 8, kAhead = 4;
+  // word maxima are loaded kAhead groups (of 128 words) ahead of their use
+  float ring[kAhead][kGroup];
 #pragma unroll
-  for (int u = 0; u < kGroup; ++u) {
-    const int wd = 32 * u + lane;
-    nxt[u] = wd < nwords ? wm[wd] : -INFINITY;
-  }
+  for (int a = 0; a < kAhead; ++a)
+#pragma unroll
+    for (int u = 0; u < kGroup; ++u) {
+      const int wd = 32 * (a * kGroup + u) + lane;
+      ring[a][u] = wd < nwords ? wm[wd] : -INFINITY;
+    }
   for (int base = 0; base < nwords; base += 32 * kGroup) {
     float cur[kGroup];
 #pragma unroll
     for (int u = 0; u < kGroup; ++u) {
-      cur[u] = nxt[u];
-      const int wd = base + 32 * (kGroup + u) + lane;
-      nxt[u] = wd < nwords ? wm[wd] : -INFINITY;
+      cur[u] = ring[0][u];
+#pragma unroll
+      for (int a = 0; a + 1 < kAhead; ++a) ring[a][u] = ring[a + 1][u];
+      const int wd = base + 32 * (kAhead * kGroup + u) + lane;
+      ring[kAhead - 1][u] = wd < nwords ? wm[wd] : -INFINITY;
     }
 #pragma unroll
     for (int u = 0; u < kGroup; ++u) {
@@ -253,6 +267,8 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __re
                                                               float* __restrict__ tags_k) {
   __shared__ float s_v[kTopkWarps][32];
   __shared__ int s_i[kTopkWarps][32];
+  __shared__ float s_logv[kTopkWarps][kLogCap];
+  __shared__ int s_logi[kTopkWarps][kLogCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kTopkWarps + warp;
   if (row >= rows) return;
@@ -263,17 +279,35 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __re
   float out_v = 0.f;
   int out_i = 0;
   bool done = false;
+  int n_logged = -1;   // >= 0: the fast pass logged every entering element of this row
   if (!force_exact) {
     SortedSink fast;
     fast.M = M; fast.lane = lane;
+    fast.log_v = s_logv[warp]; fast.log_i = s_logi[warp];
     scan_row(fast, hm, mk, wm, H, W, wpr, M, lane);
     if (!fast.ambiguous()) { out_v = fast.sv; out_i = fast.si; done = true; }
+    else n_logged = fast.n_log;
   }
   if (!done) {   // ties in play: replay the row with the exact libstdc++ heap
     HeapSink exact;
     exact.h = HeapRef{s_v[warp], s_i[warp]};
     exact.M = M; exact.lane = lane;
-    scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
+    if (n_logged >= 0 && n_logged <= kLogCap) {
+      // same entering elements, same order: build the heap from the first M elements and feed the log
+      float nv = 0.f;
+      if (lane < M) {
+        const int y = lane / W, x = lane % W;
+        const float v = hm[lane];
+        const bool keep = (mk[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+        nv = keep ? v : __fmul_rn(v, 0.0f);
+      }
+      exact.init(nv);
+      __syncwarp();
+      if (lane == 0)
+        for (int i = 0; i < n_logged; ++i) adjust_heap(exact.h, 0, M, s_logv[warp][i], s_logi[warp][i]);
+    } else {
+      scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
+    }
     __syncwarp();
     if (lane == 0) sort_heap(exact.h, M);
     __syncwarp();
