@@ -35,11 +35,14 @@ def algorithmic_bytes_per_image(size: int, flip: bool) -> int:
     return 4 * K_JOINTS * f * (q * q + h * h) + 4 * K_JOINTS * f * q * q + 4 * K_JOINTS * size * size * (1 + f)
 
 
-def make_inputs(batch: int, size: int, seed: int, unique: int = 8):
+def make_inputs(batch: int, size: int, seed: int, unique: int = 8, kind: str = "netlike"):
     """`unique` distinct synthetic images tiled to the batch (generation is CPU-bound; addresses differ,
     so tiling does not make the decode cheaper)."""
     from hpdecode import synth
-    base = synth.netlike(min(unique, batch), size, flip=True, seed=seed)[0]
+    if kind == "crowd":   # BASELINE config 4: planted 30-person scenes, grouping-bound
+        base = synth.crowd(min(unique, batch), size, persons=30, flip=True, seed=seed)[0]
+    else:
+        base = synth.netlike(min(unique, batch), size, flip=True, seed=seed)[0]
     reps = -(-batch // min(unique, batch))
     return {k: np.ascontiguousarray(np.concatenate([v] * reps)[:batch]) for k, v in base.items()}
 
@@ -96,7 +99,7 @@ def run_reference(args):
         r = synth_net.network_outputs(min(8, args.batch), args.size, flip=True, seed=1, C=32, device=dev, chunk=2)
         inputs = {k: v.contiguous().cpu().numpy() for k, v in r.items()}
     else:
-        inputs = make_inputs(min(8, args.batch), args.size, seed=1)
+        inputs = make_inputs(min(8, args.batch), args.size, seed=1, kind=args.inputs)
     pool = CpuPool(args.size, cores, inputs)
     sample = cores                                     # one image per core per step (~6 s of wall clock)
     for _ in range(args.warmup):
@@ -208,7 +211,7 @@ def run_ours(args):
         pinned = {k: v.contiguous().cpu().pin_memory() for k, v in resident.items()}
         host = {k: v[: min(8, B)].numpy() for k, v in pinned.items()}
     else:
-        host = make_inputs(B, S, seed=1 + rank)
+        host = make_inputs(B, S, seed=1 + rank, kind=args.inputs)
         pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
         resident = {k: v.to(dev) for k, v in pinned.items()}
     dec = BottomUpDecoder(K_JOINTS, MAX_PEOPLE, DET_THR, TAG_THR, dev)
@@ -354,7 +357,7 @@ def main():
     ap.add_argument("--size", type=int, default=512)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--split-priority", action="store_true")
-    ap.add_argument("--inputs", default="hrnet", choices=["hrnet", "netlike"],
+    ap.add_argument("--inputs", default="hrnet", choices=["hrnet", "netlike", "crowd"],
                     help="hrnet: outputs of a default-init HigherHRNet-W32 on seeded random images; netlike: CPU-generated fields")
     ap.add_argument("--streams", type=int, default=4, help="batches in flight per GPU (1 = strictly sequential)")
     args = ap.parse_args()

@@ -96,6 +96,8 @@ typedef struct HpdBuffers {
   float* person_scores; /* [B,M]          grouping.py:276                                        */
   int32_t* n_person;    /* [B]            persons returned (<= M)                                */
   int32_t* flags;       /* [B]            bit0: empty-scene fallback fired (grouping.py:262-269)  */
+  float* tag_bmin;      /* [B,K,HB,WPR]   HB = (H+3)/4: lower / upper bound of the first tag component over     */
+  float* tag_bmax;      /* [B,K,HB,WPR]   4 image rows x one 32-pixel word (refine prefilter; -inf/+inf = none) */
 } HpdBuffers;
 
 HPD_EXPORT int hpd_abi_version(void);
@@ -105,7 +107,7 @@ HPD_EXPORT const char* hpd_last_error_string(void);
 HPD_EXPORT int hpd_workspace_bytes(const HpdParams* p, size_t* out_bytes);
 
 /* (a)+(b) fused aggregation + NMS: model.py:85-96, results.py:46-67,225-230, grouping.py:80-83.
- * Reads scales[0..num_scales); writes agg_hm, agg_tags, nms_mask, nms_wmax, hm_wmax. */
+ * Reads scales[0..num_scales); writes agg_hm, agg_tags, nms_mask, nms_wmax, hm_wmax, tag_bmin, tag_bmax. */
 HPD_EXPORT int hpd_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const HpdBuffers* buf, void* stream);
 
 /* Standalone bilinear resize with torch's CPU arithmetic (BaseKeypointsResult.match_heatmaps_size,
@@ -115,7 +117,7 @@ HPD_EXPORT int hpd_resize_bilinear(const HpdMap* in, int batch, int channels, fl
                                    void* stream);
 
 /* (b) alone, for callers that hand in aggregated maps (MPPEHeatmapParser.parse/top_k/nms,
- * grouping.py:80-83,150): reads agg_hm; writes nms_mask, nms_wmax, hm_wmax and, if nms_out is
+ * grouping.py:80-83,150): reads agg_hm; writes nms_mask, nms_wmax, hm_wmax, tag_bmin/bmax (= no bound) and, if nms_out is
  * not NULL, the float NMS'd map [B,K,H,W] exactly as the reference's nms() returns it. */
 HPD_EXPORT int hpd_nms(const HpdParams* p, const HpdBuffers* buf, float* nms_out, void* stream);
 
@@ -128,7 +130,8 @@ HPD_EXPORT int hpd_topk(const HpdParams* p, const HpdBuffers* buf, void* stream)
 HPD_EXPORT int hpd_group(const HpdParams* p, const HpdBuffers* buf, void* stream);
 
 /* (e) adjust + person score + refine: grouping.py:172-191, :276, :193-250.
- * Reads agg_hm, agg_tags, hm_wmax, idx_k, scores_k, n_person; updates poses in place; writes person_scores. */
+ * Reads agg_hm, agg_tags, hm_wmax, tag_bmin, tag_bmax, idx_k, scores_k, n_person; updates poses in place;
+ * writes person_scores. */
 HPD_EXPORT int hpd_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* workspace, size_t workspace_bytes,
                       void* stream);
 

@@ -47,6 +47,8 @@ struct AggArgs {
   uint32_t* mask;
   float* wmax;
   float* hmax;
+  float* tmin;     // [B,K,(H+3)/4,wpr] bounds of tag component 0 per 4 rows x word
+  float* tmax;
   float* nms_out;  // standalone NMS only
   int LO_R, LO_C, HI_R, HI_C, TG_R, TG_C;
   int vec_ok;
@@ -61,6 +63,7 @@ struct AggArgs {
 __device__ __forceinline__ void nms_tile(const float* __restrict__ outT, float* __restrict__ rowM, int x0, int y0,
                                          int H, int W, int wpr, uint32_t* __restrict__ mask,
                                          float* __restrict__ wmax, float* __restrict__ hmax,
+                                         float* __restrict__ tmin, float* __restrict__ tmax,
                                          float* __restrict__ nms_out) {
   const int tid = threadIdx.x;
   for (int i = tid; i < OT_R * TW; i += kAggThreads) {
@@ -96,6 +99,11 @@ __device__ __forceinline__ void nms_tile(const float* __restrict__ outT, float* 
         mask[w] = bits;
         wmax[w] = wm;
         hmax[w] = hm;
+        if (tmin != nullptr && (y & 3) == 0) {   // this kernel derives no tag bound: "anything"
+          const size_t wb = (size_t)(y >> 2) * wpr + (x0 >> 5) + half;
+          tmin[wb] = -INFINITY;
+          tmax[wb] = INFINITY;
+        }
       }
       if (nms_out != nullptr && inside) nms_out[(size_t)y * W + x] = nv;
     }
@@ -243,7 +251,8 @@ __global__ void __launch_bounds__(kAggThreads) agg_nms_generic_kernel(const AggA
   {
     const size_t plane = (size_t)b * a.K + k;
     nms_tile(outT, rowM, x0, y0, H, W, a.wpr, a.mask + plane * H * a.wpr, a.wmax + plane * H * a.wpr,
-             a.hmax + plane * H * a.wpr, nullptr);
+             a.hmax + plane * H * a.wpr, a.tmin + plane * ((H + 3) / 4) * a.wpr, a.tmax + plane * ((H + 3) / 4) * a.wpr,
+             nullptr);
   }
   __syncthreads();
 
@@ -323,7 +332,8 @@ namespace hpd {
 // standalone NMS (grouping.py:80-83) for callers that hand in aggregated maps
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kAggThreads) nms_kernel(const float* __restrict__ hm, int K, int H, int W, int wpr,
-                                                          uint32_t* mask, float* wmax, float* hmax, float* nms_out) {
+                                                          uint32_t* mask, float* wmax, float* hmax, float* tmin, float* tmax,
+                                                          float* nms_out) {
   __shared__ float outT[OT_R * OT_C];
   __shared__ float rowM[OT_R * TW];
   const int tid = threadIdx.x;
@@ -337,7 +347,7 @@ __global__ void __launch_bounds__(kAggThreads) nms_kernel(const float* __restric
   }
   __syncthreads();
   nms_tile(outT, rowM, x0, y0, H, W, wpr, mask + plane * H * wpr, wmax + plane * H * wpr, hmax + plane * H * wpr,
-           nms_out ? nms_out + plane * H * W : nullptr);
+           tmin + plane * ((H + 3) / 4) * wpr, tmax + plane * ((H + 3) / 4) * wpr, nms_out ? nms_out + plane * H * W : nullptr);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -398,8 +408,9 @@ int check_map(const HpdMap& m, const char* name, bool required) {
 }  // namespace
 
 int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const HpdBuffers* buf, cudaStream_t st) {
-  if (!scales || !buf->agg_hm || !buf->agg_tags || !buf->nms_mask || !buf->nms_wmax || !buf->hm_wmax) {
-    set_error("hpd_aggregate_nms: scales, agg_hm, agg_tags, nms_mask, nms_wmax, hm_wmax are required");
+  if (!scales || !buf->agg_hm || !buf->agg_tags || !buf->nms_mask || !buf->nms_wmax || !buf->hm_wmax || !buf->tag_bmin ||
+      !buf->tag_bmax) {
+    set_error("hpd_aggregate_nms: scales, agg_hm, agg_tags, nms_mask, nms_wmax, hm_wmax, tag_bmin, tag_bmax are required");
     return HPD_EINVAL;
   }
   AggArgs a;
@@ -455,6 +466,8 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
   a.LO_R = LO_R; a.LO_C = LO_C | 1; a.HI_R = HI_R; a.HI_C = HI_C | 1; a.TG_C |= 1;
   a.agg_hm = buf->agg_hm; a.agg_tags = buf->agg_tags; a.mask = buf->nms_mask; a.wmax = buf->nms_wmax;
   a.hmax = buf->hm_wmax;
+  a.tmin = buf->tag_bmin;
+  a.tmax = buf->tag_bmax;
   a.tags_preflipped = p->tags_preflipped;
   a.vec_ok = (a.W % 4 == 0) && ((uintptr_t)a.agg_hm % 16 == 0) && ((uintptr_t)a.agg_tags % 16 == 0);
 
@@ -504,14 +517,14 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
 }
 
 int launch_nms(const HpdParams* p, const HpdBuffers* buf, float* nms_out, cudaStream_t st) {
-  if (!buf->agg_hm || !buf->nms_mask || !buf->nms_wmax || !buf->hm_wmax) {
-    set_error("hpd_nms: agg_hm, nms_mask, nms_wmax, hm_wmax are required");
+  if (!buf->agg_hm || !buf->nms_mask || !buf->nms_wmax || !buf->hm_wmax || !buf->tag_bmin || !buf->tag_bmax) {
+    set_error("hpd_nms: agg_hm, nms_mask, nms_wmax, hm_wmax, tag_bmin, tag_bmax are required");
     return HPD_EINVAL;
   }
   const int H = p->out_h, W = p->out_w, wpr = (W + 31) / 32;
   const dim3 grid((W + TW - 1) / TW, (H + TH - 1) / TH, p->batch * p->num_kpts);
   nms_kernel<<<grid, kAggThreads, 0, st>>>(buf->agg_hm, p->num_kpts, H, W, wpr, buf->nms_mask, buf->nms_wmax,
-                                           buf->hm_wmax, nms_out);
+                                           buf->hm_wmax, buf->tag_bmin, buf->tag_bmax, nms_out);
   count_launch();
   return check_launch("nms_kernel");
 }

@@ -216,11 +216,14 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
     const float wa0 = x_first ? 1.f : 0.375f, wb0 = x_first ? 0.f : 0.625f;
     const float wa1 = x_first ? 1.f : 0.125f, wb1 = x_first ? 0.f : 0.875f;
     float hA[E][4], hB[E][4];
-    auto hpass = [&](int r, float (&h)[E][4]) {
+    // also returns the range of the sources of the FIRST tag component: every output it contributes to
+    // is a convex combination of them (refine prefilter, tag_bmin / tag_bmax)
+    auto hpass = [&](int r, float (&h)[E][4], float& mn, float& mx) {
 #pragma unroll
       for (int e = 0; e < E; ++e) {
         const float* t = sT + e * TR * tc + r * tc + tb;
         const float t0 = t[0], t1 = t[1], t2 = t[2];
+        if (e == 0) { mn = fminf(fminf(t0, t1), t2); mx = fmaxf(fmaxf(t0, t1), t2); }
         const float a0 = x_first ? t1 : t0, b0 = x_first ? t2 : t1;
         h[e][0] = fmaf(wa0, a0, __fmul_rn(wb0, b0));
         h[e][1] = fmaf(wa1, a0, __fmul_rn(wb1, b0));
@@ -246,17 +249,21 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
     };
     // tile rows: r <-> quarter-res row tyo + r = y0/4 - 1 + r.  Rows y0, y0+1 use (i-1, i) with
     // i = y0/4, i.e. tile rows (0, 1); then each group of 4 rows 4i+2..4i+5 uses rows (i, i+1).
-    hpass(0, hA);
-    hpass(1, hB);
+    const unsigned amask = __activemask();      // W % 32 == 0: whole 8-lane word groups are active
+    float mnA, mxA, mnB, mxB, mnC, mxC;
+    hpass(0, hA, mnA, mxA);
+    hpass(1, hB, mnB, mxB);
     if (y0 == 0) {          // first two rows of the image: src clamps to 0 -> taps (row 0, row 1), weights (1, 0)
       float hC[E][4];
-      hpass(2, hC);         // tile row 1 = image row 0, tile row 2 = image row 1
+      hpass(2, hC, mnC, mxC);   // tile row 1 = image row 0, tile row 2 = image row 1
       emit(0, 1.f, 0.f, hB, hC);
       emit(1, 1.f, 0.f, hB, hC);
     } else {
       emit(y0, 0.375f, 0.625f, hA, hB);
       emit(y0 + 1, 0.125f, 0.875f, hA, hB);
     }
+    const int HB = (H + 3) >> 2;
+    const size_t bbase = (((size_t)b * a.K + k) * HB + (y0 >> 2)) * a.wpr + (X0 >> 5);
 #pragma unroll 1
     for (int g = 0; g < RB / 4; ++g) {
       // rows y0 + 4g + 2 .. y0 + 4g + 5 : taps (tile row g+1, tile row g+2)
@@ -264,7 +271,21 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
       for (int e = 0; e < E; ++e)
 #pragma unroll
         for (int c = 0; c < 4; ++c) hA[e][c] = hB[e][c];
-      hpass(g + 2, hB);
+      hpass(g + 2, hB, mnC, mxC);
+      // band of rows y0+4g .. y0+4g+3 reads tile rows g, g+1, g+2: bounds over the 8 lanes of the word
+      if (y0 + 4 * g < H) {
+        float mn = fminf(fminf(mnA, mnB), mnC), mx = fmaxf(fmaxf(mxA, mxB), mxC);
+#pragma unroll
+        for (int o = 1; o < 8; o <<= 1) {
+          mn = fminf(mn, __shfl_xor_sync(amask, mn, o));
+          mx = fmaxf(mx, __shfl_xor_sync(amask, mx, o));
+        }
+        if ((lane & 7) == 0) {
+          a.tmin[bbase + (size_t)g * a.wpr] = mn;
+          a.tmax[bbase + (size_t)g * a.wpr] = mx;
+        }
+      }
+      mnA = mnB; mxA = mxB; mnB = mnC; mxB = mxC;
       const int y = y0 + 4 * g + 2;
       emit(y, 0.875f, 0.125f, hA, hB);
       emit(y + 1, 0.625f, 0.375f, hA, hB);

@@ -165,6 +165,8 @@ constexpr int kScanWordsPerBlock = 1024;
 __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const float* __restrict__ agg_hm,
                                                                       const float* __restrict__ agg_tags,
                                                                       const float* __restrict__ hmax,
+                                                                      const float* __restrict__ tag_bmin,
+                                                                      const float* __restrict__ tag_bmax,
                                                                       const float* __restrict__ scores_k, int pass_id,
                                                                       int K, int M, int E, int H, int W, int wpr,
                                                                       RefineWs ws) {
@@ -180,6 +182,9 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
   const float* m = agg_hm + (size_t)bk * H * W;
   const float* t = agg_tags + (size_t)bk * H * W * E;
   const float* hx = hmax + (size_t)bk * nwords;
+  const int HB = (H + 3) >> 2;
+  const float* tlo = tag_bmin + (size_t)bk * HB * wpr;
+  const float* thi = tag_bmax + (size_t)bk * HB * wpr;
   const float split = scores_k[(size_t)bk * M + M - 1];
   unsigned long long* gkeys = ws.keys + (size_t)bk * M;
 
@@ -196,15 +201,42 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
     const int wd = base + lane;
     const float hv = wd < w_end ? hx[wd] : -INFINITY;
     if (lane < cnt) best = __ldcg(gkeys + lane);           // newest bests of all warps working on this joint
-    // a word matters if its raw maximum can reach the smallest running best among the pairs
-    unsigned thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
-    const bool mine = (pass_id == 0) ? (hv >= split) : !(hv >= split);
-    uint32_t pass = __ballot_sync(kFull, wd < w_end && mine && ordered_u32(__fadd_rn(hv, 0.0f)) >= thr);
+    // A word matters to a pair if  max(hm) - rint(min distance to the pair's tag)  can reach the pair's
+    // running best: the distance is bounded from below through the band's range of the first tag
+    // component (tag_bmin / tag_bmax, minus a slack that covers the rounding of the interpolation).
+    float lo = 0.f, hi = 0.f;
+    if (wd < w_end) {
+      const int yw = wd / wpr;
+      const int bi = (yw >> 2) * wpr + (wd - yw * wpr);
+      lo = tlo[bi];
+      hi = thi[bi];
+    }
+    auto reach = [&](float hmx, float lo_, float hi_, float Tq) {   // ordered upper bound of the value
+      const float slack = 1e-4f * (1.f + fabsf(Tq) + fmaxf(fabsf(lo_), fabsf(hi_)));
+      const float dmin = fmaxf(fmaxf(fmaxf(lo_ - Tq, Tq - hi_), 0.f) - slack, 0.f);
+      return ordered_u32(__fadd_rn(__fsub_rn(hmx, rintf(dmin)), 0.0f));
+    };
+    const bool mine = wd < w_end && ((pass_id == 0) ? (hv >= split) : !(hv >= split));
+    // cheap test first: the word's maximum against the smallest running best of all pairs
+    const unsigned thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
+    const unsigned hv_o = ordered_u32(__fadd_rn(hv, 0.0f));
+    if (!__any_sync(kFull, mine && hv_o >= thr)) continue;
+    const unsigned chunk_max = __reduce_max_sync(kFull, mine ? hv_o : 0u);
+    bool viable = false;
+    for (int q = 0; q < cnt; ++q) {
+      const unsigned bq = (unsigned)(__shfl_sync(kFull, best, q) >> 32);
+      if (bq > chunk_max) continue;                       // no word of this chunk reaches pair q
+      const float Tq = __shfl_sync(kFull, T0, q);
+      viable = viable || (reach(hv, lo, hi, Tq) >= bq);
+    }
+    uint32_t pass = __ballot_sync(kFull, mine && viable);
     while (pass) {
       const int l = __ffs(pass) - 1;
       pass &= pass - 1;
-      const unsigned hw_o = ordered_u32(__fadd_rn(__shfl_sync(kFull, hv, l), 0.0f));
-      if (hw_o < thr) continue;
+      const float hw_f = __shfl_sync(kFull, hv, l), lo_l = __shfl_sync(kFull, lo, l), hi_l = __shfl_sync(kFull, hi, l);
+      // only the pairs this word can still reach
+      uint32_t todo = __ballot_sync(kFull, lane < cnt && reach(hw_f, lo_l, hi_l, T0) >= (unsigned)(best >> 32));
+      if (!todo) continue;
       const int w2 = base + l;
       const int y = w2 / wpr, x0 = (w2 - y * wpr) * 32;
       const bool valid = x0 + lane < W;
@@ -216,8 +248,6 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
         if (E > 1) t1 = t[(size_t)idx * E + 1];
       }
       bool improved = false;
-      // only the pairs whose running best this word's maximum can still reach
-      uint32_t todo = __ballot_sync(kFull, lane < cnt && hw_o >= (unsigned)(best >> 32));
       while (todo) {
         const int q = __ffs(todo) - 1;
         todo &= todo - 1;
@@ -225,18 +255,15 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
         const float v = refine_value(pv, t0, t1, __shfl_sync(kFull, T0, q), __shfl_sync(kFull, T1, q), E);
         const unsigned vo = valid ? ordered_u32(v) : 0u;
         if (!__any_sync(kFull, vo >= (unsigned)(bq >> 32))) continue;
-        const unsigned hi = __reduce_max_sync(kFull, vo);
-        const int first = __ffs(__ballot_sync(kFull, vo == hi)) - 1;      // lowest index among equal values
-        const unsigned long long wbest = ((unsigned long long)hi << 32) | (unsigned)(~(unsigned)(y * W + x0 + first));
+        const unsigned vmax = __reduce_max_sync(kFull, vo);
+        const int first = __ffs(__ballot_sync(kFull, vo == vmax)) - 1;    // lowest index among equal values
+        const unsigned long long wbest = ((unsigned long long)vmax << 32) | (unsigned)(~(unsigned)(y * W + x0 + first));
         if (wbest > bq) {
           if (lane == q) best = wbest;
           improved = true;
         }
       }
-      if (improved) {
-        if (lane < cnt) atomicMax(gkeys + lane, best);
-        thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
-      }
+      if (improved && lane < cnt) atomicMax(gkeys + lane, best);
     }
   }
 }
@@ -270,8 +297,8 @@ size_t refine_workspace_bytes(const HpdParams* p) {
 }
 
 int launch_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* wsp, size_t ws_bytes, cudaStream_t st) {
-  if (!buf->agg_hm || !buf->agg_tags || !buf->hm_wmax || !buf->idx_k || !buf->scores_k || !buf->poses ||
-      !buf->person_scores || !buf->n_person) {
+  if (!buf->agg_hm || !buf->agg_tags || !buf->hm_wmax || !buf->tag_bmin || !buf->tag_bmax || !buf->idx_k || !buf->scores_k ||
+      !buf->poses || !buf->person_scores || !buf->n_person) {
     set_error("hpd_adjust_refine: agg_hm, agg_tags, hm_wmax, idx_k, scores_k, poses, person_scores, n_person are required");
     return HPD_EINVAL;
   }
@@ -294,7 +321,7 @@ int launch_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* wsp, s
   const int nwords = H * wpr;
   const dim3 grid((nwords + kScanWordsPerBlock - 1) / kScanWordsPerBlock, B * K);
   for (int pass_id = 0; pass_id < 2; ++pass_id) {
-    refine_scan_kernel<<<grid, kScanWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->hm_wmax, buf->scores_k, pass_id,
+    refine_scan_kernel<<<grid, kScanWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->hm_wmax, buf->tag_bmin, buf->tag_bmax, buf->scores_k, pass_id,
                                                          K, M, E, H, W, wpr, ws);
     count_launch();
     if ((rc = check_launch("refine_scan_kernel"))) return rc;

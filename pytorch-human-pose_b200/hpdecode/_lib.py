@@ -43,7 +43,7 @@ class HpdParams(ctypes.Structure):
 class HpdBuffers(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "agg_hm", "agg_tags", "nms_mask", "nms_wmax", "hm_wmax", "scores_k", "idx_k", "coords_k", "tags_k",
-        "poses", "person_scores", "n_person", "flags")]
+        "poses", "person_scores", "n_person", "flags", "tag_bmin", "tag_bmax")]
 
 
 class HpdError(RuntimeError):

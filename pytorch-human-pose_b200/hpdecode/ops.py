@@ -87,6 +87,8 @@ class DecodeBuffers:
         self.nms_mask = torch.empty((B, K, H, wpr), **i32)
         self.nms_wmax = torch.empty((B, K, H, wpr), **f32)
         self.hm_wmax = torch.empty((B, K, H, wpr), **f32)
+        self.tag_bmin = torch.empty((B, K, (H + 3) // 4, wpr), **f32)
+        self.tag_bmax = torch.empty((B, K, (H + 3) // 4, wpr), **f32)
         self.scores_k = torch.empty((B, K, M), **f32)
         self.idx_k = torch.empty((B, K, M), **i32)
         self.coords_k = torch.empty((B, K, M, 2), **i32)
@@ -266,7 +268,7 @@ def group_op(tags_k: Tensor, coords_k: Tensor, scores_k: Tensor, det_thr: float,
     bufs = DecodeBuffers.__new__(DecodeBuffers)
     params = make_params(B, K, out_h, out_w, E, M, det_thr, tag_thr)
     z = torch.empty((0,), device=dev)
-    bufs.agg_hm = bufs.agg_tags = bufs.nms_wmax = bufs.hm_wmax = bufs.person_scores = z
+    bufs.agg_hm = bufs.agg_tags = bufs.nms_wmax = bufs.hm_wmax = bufs.person_scores = bufs.tag_bmin = bufs.tag_bmax = z
     bufs.nms_mask = bufs.idx_k = torch.empty((0,), device=dev, dtype=torch.int32)
     bufs.scores_k, bufs.coords_k, bufs.tags_k = scores_k.contiguous(), coords_k.contiguous().int(), tags_k.contiguous()
     bufs.poses = torch.empty((B, M, K, 3 + E), device=dev, dtype=torch.float32)
