@@ -140,3 +140,42 @@ def test_pipeline_gives_the_same_results_as_sequential_decode():
     for w, g in zip(want, got):
         for (wg, wp), (gg, gp) in zip(w, g):
             assert np.array_equal(_bits(wg), _bits(gg)) and np.array_equal(_bits(wp), _bits(gp))
+
+
+def test_nonsquare_other_joint_count_and_m20(oracle):
+    """Edge shapes through the whole path: H != W (both kernels' strides), K = 8 joints (identity joint order),
+    M = 20 with the validation thresholds, E = 1, batch with very different person counts."""
+    from hpdecode import BottomUpDecoder
+    H, W, K, M = 256, 384, 8, 20
+    rng = np.random.default_rng(7)
+    B = 3
+    lo = (rng.standard_normal((B, K, H // 4, W // 4)) * 0.05).astype(np.float32)
+    hi = (rng.standard_normal((B, K, H // 2, W // 2)) * 0.05).astype(np.float32)
+    tag = (rng.standard_normal((B, K, H // 4, W // 4)) * 0.02).astype(np.float32)
+    for b, persons in enumerate((0, 3, 25)):          # image 0 stays below det_thr -> empty-scene fallback
+        for p in range(persons):
+            for k in range(K):
+                y, x = rng.integers(3, H // 4 - 3), rng.integers(3, W // 4 - 3)
+                lo[b, k, y, x] += 0.6 + 0.3 * rng.random()
+                hi[b, k, 2 * y:2 * y + 2, 2 * x:2 * x + 2] += 0.5
+                tag[b, k, y - 1:y + 2, x - 1:x + 2] = 1.5 * p
+    lo[0] = np.minimum(lo[0], 0.01)
+    hi[0] = np.minimum(hi[0], 0.01)
+    scale = {"hm_lo": lo, "hm_hi": hi, "tag": tag}
+    dec = BottomUpDecoder(K, M, 0.1, 1.0, "cuda:0")
+    res = dec.decode([{k: torch.from_numpy(v).cuda() for k, v in scale.items()}], (H, W))
+    out = res.to_numpy()
+    assert int(res.flags[0].item()) == 1 and out[0][0].dtype == np.float64 and out[0][0].shape == (1, K, 4)
+    for b in range(B):
+        hm_o, tg_o = oracle.aggregate([{k: v[b] for k, v in scale.items()}], (H, W), flip_index=list(range(K)))
+        assert np.array_equal(_bits(res.agg_hm[b].cpu().numpy()), _bits(hm_o))
+        assert np.array_equal(_bits(res.agg_tags[b].cpu().numpy()), _bits(tg_o))
+        ref = oracle.parse(hm_o, tg_o, M, 0.1, 1.0)
+        assert np.array_equal(res.bufs.idx_k[b].cpu().numpy(), ref["idx_k"])
+        if ref["fallback"]:
+            from hpdecode.decoder import _finish
+            gj, ps = _finish(ref["grouped_joints"], ref["person_scores"], 1)
+            assert np.array_equal(out[b][0], gj) and np.array_equal(out[b][1], ps)
+        else:
+            assert np.array_equal(_bits(out[b][0]), _bits(ref["grouped_joints"]))
+            assert np.array_equal(_bits(out[b][1]), _bits(ref["person_scores"]))
