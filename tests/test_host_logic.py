@@ -76,3 +76,22 @@ def test_gather_packed_world2_gloo():
         p.join(timeout=120)
         assert p.exitcode == 0
     assert np.array_equal(got, np.arange(15, dtype=np.float32).reshape(5, 3))
+
+
+def test_back_projection_and_coco_records():
+    """results.py:158-201 + eval.py:31-47 on the host: identity-like transform keeps coordinates, records
+    have the COCO layout."""
+    from hpdecode.coco import batch_to_coco, coco_records
+    from hpdecode.transforms import affine_transform, get_affine_transform
+    m = get_affine_transform((256, 256), (512.0, 512.0), 0, (512, 512), inverse=True)
+    assert m.shape == (2, 3) and np.allclose(affine_transform([10.0, 20.0], m), [10.0, 20.0], atol=1e-4)
+    m2 = get_affine_transform((320, 240), (640.0, 480.0), 0, (512, 384), inverse=True)      # 0.8x network input
+    assert np.allclose(affine_transform([256.0, 192.0], m2), [320.0, 240.0], atol=1e-3)
+    grouped = np.zeros((2, 17, 4), np.float32)
+    grouped[..., 0] = 100.0
+    grouped[..., 1] = 50.0
+    recs = batch_to_coco([7], [(grouped, np.array([0.5, 0.25], np.float32))], [(256, 256)], [(512.0, 512.0)], (512, 512))
+    assert len(recs) == 2 and recs[0]["image_id"] == 7 and recs[0]["category_id"] == 1
+    assert len(recs[0]["keypoints"]) == 51 and recs[0]["keypoints"][2] == 1 and abs(recs[0]["keypoints"][0] - 100.0) < 1e-3
+    assert recs[1]["score"] == 0.25
+    assert coco_records(1, np.zeros((0, 17, 2)), np.zeros((0,))) == []

@@ -34,3 +34,22 @@ def test_oracles_match_unmodified_reference(gen, kw, size, M, det, tthr, oracle)
     assert np.array_equal(_bits(O["person_scores"]), _bits(R["person_scores"]))
     gj, ps = py_port.parse(hm_t, tg_t, M, det, tthr)
     assert np.array_equal(gj, R["grouped_joints"]) and np.array_equal(ps, R["person_scores"])
+
+
+def test_back_projection_matches_reference_functions():
+    """hpdecode.transforms vs the reference's base/transforms/utils.py:5-57 loaded from /root/reference."""
+    import importlib.util
+    from hpdecode.transforms import affine_transform, get_affine_transform
+    spec = importlib.util.spec_from_file_location("ref_tu", ref_runner.REFERENCE_ROOT + "/src/base/transforms/utils.py")
+    ref = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(ref)
+    rng = np.random.default_rng(0)
+    for _ in range(100):
+        c = (int(rng.integers(100, 900)), int(rng.integers(100, 700)))
+        s = (float(rng.uniform(200, 1200)), float(rng.uniform(200, 1200)))
+        o = (int(rng.choice([512, 640, 704])), int(rng.choice([512, 384, 640])))
+        for inv in (False, True):
+            a, b = ref.get_affine_transform(c, s, 0, o, inverse=inv), get_affine_transform(c, s, 0, o, inverse=inv)
+            assert np.array_equal(a, b)
+            p = [float(rng.uniform(0, 500)), float(rng.uniform(0, 500))]
+            assert np.array_equal(ref.affine_transform(p, a), affine_transform(p, b))
