@@ -183,51 +183,77 @@ __global__ void __launch_bounds__(kAggThreads) agg_nms_generic_kernel(const AggA
     {
       const float* p = S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc;
       const float* pf = S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr;
-      for (int i = tid; i < nly * nlx; i += kAggThreads) {
-        const int r = i / nlx, c = i % nlx;
-        const int y = lya + r, x = lxa + c;
-        float v = p[(size_t)y * S.lw + x];
-        if (pf) v = __fmul_rn(__fadd_rn(v, pf[(size_t)y * S.lw + (S.lw - 1 - x)]), 0.5f);
-        loT[r * a.LO_C + c] = v;
-      }
+      const int per = min(nlx, kAggThreads), groups = kAggThreads / per;
+      const int rg = tid / per;
+      if (rg < groups)
+        for (int c = tid % per; c < nlx; c += per) {
+          const int x = lxa + c;
+          for (int r = rg; r < nly; r += groups) {
+            const int rowo = (lya + r) * S.lw;
+            float v = p[rowo + x];
+            if (pf) v = __fmul_rn(__fadd_rn(v, pf[rowo + (S.lw - 1 - x)]), 0.5f);
+            loT[r * a.LO_C + c] = v;
+          }
+        }
     }
     {
       const float* p = S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc;
       const float* pf = S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr;
-      for (int i = tid; i < nhy * nhx; i += kAggThreads) {
-        const int r = i / nhx, c = i % nhx;
-        const int y = hya + r, x = hxa + c;
-        float v = p[(size_t)y * S.hw + x];
-        if (pf) v = __fmul_rn(__fadd_rn(v, pf[(size_t)y * S.hw + (S.hw - 1 - x)]), 0.5f);
-        hiT[r * a.HI_C + c] = v;
-      }
+      const int per = min(nhx, kAggThreads), groups = kAggThreads / per;
+      const int rg = tid / per;
+      if (rg < groups)
+        for (int c = tid % per; c < nhx; c += per) {
+          const int x = hxa + c;
+          for (int r = rg; r < nhy; r += groups) {
+            const int rowo = (hya + r) * S.hw;
+            float v = p[rowo + x];
+            if (pf) v = __fmul_rn(__fadd_rn(v, pf[rowo + (S.hw - 1 - x)]), 0.5f);
+            hiT[r * a.HI_C + c] = v;
+          }
+        }
     }
     __syncthreads();
-    // stage mean at the high stage's resolution (results.py:225-226), in place
-    for (int i = tid; i < nhy * nhx; i += kAggThreads) {
-      const int r = i / nhx, c = i % nhx;
-      const float* r0 = loT + hr_i0[r] * a.LO_C;
-      const float* r1 = loT + hr_i1[r] * a.LO_C;
-      const int c0 = hc_i0[c], c1 = hc_i1[c];
-      const float up = lerp2(hc_w0[c], hc_w1[c], hr_w0[r], hr_w1[r], r0[c0], r0[c1], r1[c0], r1[c1]);
-      hiT[r * a.HI_C + c] = __fmul_rn(__fadd_rn(up, hiT[r * a.HI_C + c]), 0.5f);
+    // stage mean at the high stage's resolution (results.py:225-226), in place.  A thread owns one column
+    // (its taps stay in registers) and strides over the rows.
+    {
+      const int per = min(nhx, kAggThreads), groups = kAggThreads / per;
+      const int rg = tid / per;
+      if (rg < groups)
+        for (int c = tid % per; c < nhx; c += per) {
+          const int c0 = hc_i0[c], c1 = hc_i1[c];
+          const float cw0 = hc_w0[c], cw1 = hc_w1[c];
+          for (int r = rg; r < nhy; r += groups) {
+            const float* r0 = loT + hr_i0[r] * a.LO_C;
+            const float* r1 = loT + hr_i1[r] * a.LO_C;
+            const float up = lerp2(cw0, cw1, hr_w0[r], hr_w1[r], r0[c0], r0[c1], r1[c0], r1[c1]);
+            hiT[r * a.HI_C + c] = __fmul_rn(__fadd_rn(up, hiT[r * a.HI_C + c]), 0.5f);
+          }
+        }
     }
     __syncthreads();
-    // full-resolution tile with halo (results.py:227); scales accumulate sequentially
-    for (int i = tid; i < OT_R * OT_C; i += kAggThreads) {
-      const int r = i / OT_C, c = i % OT_C;
-      float v;
-      if (or_i0[r] < 0 || oc_i0[c] < 0) {
-        v = -INFINITY;
-      } else {
-        const float* r0 = hiT + or_i0[r] * a.HI_C;
-        const float* r1 = hiT + or_i1[r] * a.HI_C;
-        const int c0 = oc_i0[c], c1 = oc_i1[c];
-        v = lerp2(oc_w0[c], oc_w1[c], or_w0[r], or_w1[r], r0[c0], r0[c1], r1[c0], r1[c1]);
-        if (s > 0) v = __fadd_rn(outT[i], v);
-        if (a.n_scales > 1 && s == a.n_scales - 1) v = __fdiv_rn(v, (float)a.n_scales);
+    // full-resolution tile with halo (results.py:227); scales accumulate sequentially.  Column-owned too.
+    {
+      constexpr int kGroups = kAggThreads / OT_C;   // 3 row groups of OT_C threads
+      const int c = tid % OT_C, rg = tid / OT_C;
+      if (rg < kGroups) {
+        const int c0 = oc_i0[c];
+        const int c1 = c0 >= 0 ? oc_i1[c] : 0;
+        const float cw0 = c0 >= 0 ? oc_w0[c] : 0.f, cw1 = c0 >= 0 ? oc_w1[c] : 0.f;
+        const bool last = a.n_scales > 1 && s == a.n_scales - 1;
+        const float nsc = (float)a.n_scales;
+        for (int r = rg; r < OT_R; r += kGroups) {
+          const int ri0 = or_i0[r];
+          float v = -INFINITY;
+          if (ri0 >= 0 && c0 >= 0) {
+            const float* r0 = hiT + ri0 * a.HI_C;
+            const float* r1 = hiT + or_i1[r] * a.HI_C;
+            v = lerp2(cw0, cw1, or_w0[r], or_w1[r], r0[c0], r0[c1], r1[c0], r1[c1]);
+            if (s > 0) v = __fadd_rn(outT[r * OT_C + c], v);
+            if (last) v = __fdiv_rn(v, nsc);
+          }
+          outT[r * OT_C + c] = v;
+        }
       }
-      outT[i] = v;
     }
     __syncthreads();
   }
