@@ -122,10 +122,16 @@ def run_reference(args):
 
 
 def workload_config(args):
+    in_mb = args.batch * (algorithmic_bytes_per_image(args.size, True) - 4 * K_JOINTS * args.size * args.size * 3) / 1e6
+    out_mb = args.batch * 4 * K_JOINTS * args.size * args.size * 3 / 1e6
+    l2 = ("inputs (%.0f MB/batch) and outputs (%.0f MB/batch) exceed the 126 MB L2; no flush needed" % (in_mb, out_mb)
+          if in_mb + out_mb > 4 * 126 else
+          "working set %.0f MB/batch is comparable to the 126 MB L2 and is NOT flushed between steps: use the default "
+          "batch for roofline numbers" % (in_mb + out_mb))
     return {"workload": f"HigherHRNet-W32 {args.size}x{args.size}, batch {args.batch} per GPU, flip test, single scale "
                         "(BASELINE configs[2], sharded by image)",
-            "batch_per_gpu": args.batch, "size": args.size, "flip": True, "max_people": MAX_PEOPLE,
-            "l2": "inputs (855 MB/batch) and outputs (3.4 GB/batch) exceed the 126 MB L2; no flush needed"}
+            "batch_per_gpu": args.batch, "size": args.size, "flip": True, "max_people": MAX_PEOPLE, "inputs": args.inputs,
+            "l2": l2}
 
 
 # ------------------------------------------------------------------------------------------------
