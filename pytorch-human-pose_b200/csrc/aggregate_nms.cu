@@ -54,6 +54,7 @@ struct AggArgs {
   int vec_ok;
   int tags_preflipped;
   int in_vec_ok;   // inputs allow 16-byte loads (aligned bases, strides multiples of 4 elements)
+  int in_vec_ok_all;   // ... for every scale
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -351,6 +352,7 @@ __global__ void __launch_bounds__(kAggThreads) agg_nms_generic_kernel(const AggA
 }  // namespace hpd
 namespace hpd {
 #include "aggregate_nms_x2.cuh"
+#include "aggregate_nms_ms.cuh"
 }  // namespace hpd
 namespace hpd {
 
@@ -495,6 +497,15 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
   a.tmin = buf->tag_bmin;
   a.tmax = buf->tag_bmax;
   a.tags_preflipped = p->tags_preflipped;
+  {
+    auto okp = [](const float* q, long long sb, long long sc_) { return q == nullptr || ((uintptr_t)q % 16 == 0 && sb % 4 == 0 && sc_ % 4 == 0); };
+    a.in_vec_ok_all = 1;
+    for (int s = 0; s < a.n_scales; ++s) {
+      const ScaleDev& S = a.sc[s];
+      if (!(okp(S.lo, S.lo_sb, S.lo_sc) && okp(S.hi, S.hi_sb, S.hi_sc) && okp(S.lo_f, S.lof_sb, S.lof_sc) && okp(S.hi_f, S.hif_sb, S.hif_sc)))
+        a.in_vec_ok_all = 0;
+    }
+  }
   a.vec_ok = (a.W % 4 == 0) && ((uintptr_t)a.agg_hm % 16 == 0) && ((uintptr_t)a.agg_tags % 16 == 0);
 
   // standard single-scale x2/x2/x4 layout -> specialised kernel (aggregate_nms_x2.cuh)
@@ -523,6 +534,64 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
 #undef HPD_X2_LAUNCH
       count_launch();
       return check_launch("agg_nms_x2_kernel");
+    }
+  }
+  // several scales and / or other hi -> output ratios with the HigherHRNet structure (lo -> hi exactly x2,
+  // tags exactly x4) -> column-walking multi-scale kernel (aggregate_nms_ms.cuh)
+  {
+    bool ok = !p->force_generic && a.n_scales <= 3 && a.in_vec_ok_all && a.th * 4 == a.H && a.tw * 4 == a.W && a.W % 32 == 0 && a.H % 4 == 0 &&
+              a.W >= 256 && a.vec_ok;
+    for (int s = 0; ok && s < a.n_scales; ++s) {
+      const ScaleDev& S = a.sc[s];
+      ok = S.hh == 2 * S.lh && S.hw == 2 * S.lw && S.lh >= 2 && S.lw >= 4 && S.lw % 4 == 0;
+    }
+    if (ok) {
+      const int NW = a.W >= 512 ? 4 : 2;
+      ms::Geom g;
+      memset(&g, 0, sizeof(g));
+      int off = 0;
+      for (int s = 0; s < a.n_scales; ++s) {
+        const ScaleDev& S = a.sc[s];
+        int hc, lc, hr, lr;
+        axis_extents(a.W, 128 * NW, 2, S.hw, S.s_hi_x, S.lw, S.s_lo_x, &hc, &lc);
+        axis_extents(a.H, ms::RB, 2, S.hh, S.s_hi_y, S.lh, S.s_lo_y, &hr, &lr);
+        g.off_s[s] = off;
+        g.hr[s] = hr;
+        g.hc[s] = (hc + 6 + 3) & ~3;      // origin rounded down / width rounded up to 4 in the kernel
+        off += g.hr[s] * g.hc[s];
+        g.lr = lr > g.lr ? lr : g.lr;
+        lc = (lc + 6 + 3) & ~3;
+        g.lc = lc > g.lc ? lc : g.lc;
+        g.hr_max = hr > g.hr_max ? hr : g.hr_max;
+      }
+      const int tag_words = a.E * ms::TR * (32 * NW + 8);
+      off = off > tag_words ? off : tag_words;
+      off = (off + 3) & ~3;
+      g.off_lo = off;   off += (g.lr * g.lc + 3) & ~3;
+      g.off_edge = off; off += NW * ms::NROWS * 4;
+      g.off_tab = off;  off += 4 * a.n_scales * ms::NROWS;
+      g.off_rt2 = off;  off += 4 * g.hr_max;
+      g.total = off;
+      const size_t smem = sizeof(float) * (size_t)g.total;
+      if (smem <= 200 * 1024) {
+        const dim3 grid((a.W + 128 * NW - 1) / (128 * NW), (a.H + ms::RB - 1) / ms::RB, a.B * a.K);
+#define HPD_MS_LAUNCH(E_, NW_, NS_)                                                                              \
+  do {                                                                                                           \
+    if (smem > 48 * 1024)                                                                                        \
+      cudaFuncSetAttribute(ms::agg_nms_ms_kernel<E_, NW_, NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    ms::agg_nms_ms_kernel<E_, NW_, NS_><<<grid, 32 * NW_, smem, st>>>(a, g);                                     \
+  } while (0)
+#define HPD_MS_NS(E_, NW_)                                                                                       \
+  do {                                                                                                           \
+    if (a.n_scales == 1) HPD_MS_LAUNCH(E_, NW_, 1); else if (a.n_scales == 2) HPD_MS_LAUNCH(E_, NW_, 2); else HPD_MS_LAUNCH(E_, NW_, 3); \
+  } while (0)
+        if (a.E == 1) { if (NW == 4) HPD_MS_NS(1, 4); else HPD_MS_NS(1, 2); }
+        else          { if (NW == 4) HPD_MS_NS(2, 4); else HPD_MS_NS(2, 2); }
+#undef HPD_MS_NS
+#undef HPD_MS_LAUNCH
+        count_launch();
+        return check_launch("agg_nms_ms_kernel");
+      }
     }
   }
   const int lo_words = (a.LO_R * a.LO_C > a.E * a.TG_R * a.TG_C) ? a.LO_R * a.LO_C : a.E * a.TG_R * a.TG_C;

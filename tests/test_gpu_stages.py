@@ -194,3 +194,43 @@ def test_topk_fast_path_equals_exact_heap_replay(gen, kw, size):
         outs.append((bufs.idx_k.cpu().numpy(), bufs.scores_k.cpu().numpy(), bufs.tags_k.cpu().numpy()))
     assert np.array_equal(outs[0][0], outs[1][0])
     assert np.array_equal(_bits(outs[0][1]), _bits(outs[1][1])) and np.array_equal(_bits(outs[0][2]), _bits(outs[1][2]))
+
+
+def _ms_scales(B, H, W, ratios, flip, seed):
+    """Network outputs for several test scales: hi at ratio*(H, W), lo / tag at half of that."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for r in ratios:
+        hh, hw = int(round(H * r)), int(round(W * r))
+        d = {"hm_lo": torch.randn(B, 17, hh // 2, hw // 2, generator=g), "hm_hi": torch.randn(B, 17, hh, hw, generator=g),
+             "tag": torch.randn(B, 17, hh // 2, hw // 2, generator=g)}
+        if flip:
+            d.update({k + "_f": torch.randn_like(v) for k, v in list(d.items())})
+        out.append({k: v.cuda() for k, v in d.items()})
+    return out
+
+
+@pytest.mark.parametrize("H,W,ratios,tag_scale,flip,B", [
+    (512, 512, (0.25, 0.5, 0.75), 1, True, 2),      # BASELINE config 3 ratios (scales 0.5 / 1.0 / 1.5)
+    (640, 640, (0.25, 0.5, 0.75), 1, True, 1),
+    (256, 384, (0.5, 0.75), 0, False, 1),           # two scales, non-square, E = 1, NW = 2
+    (512, 768, (0.5, 1.0), 0, True, 1),             # hi == output size (copy taps), several CTAs per row
+    (320, 512, (0.25, 0.5), 1, True, 1),            # H not a multiple of 64
+])
+def test_multiscale_kernel_is_bit_identical_to_generic(H, W, ratios, tag_scale, flip, B):
+    scales = _ms_scales(B, H, W, ratios, flip, seed=H + W)
+    E = 2 if flip else 1
+    fast = _run_aggregate(scales, H, W, E, False, tag_scale=tag_scale)
+    slow = _run_aggregate(scales, H, W, E, True, tag_scale=tag_scale)
+    for name in ("agg_hm", "agg_tags", "nms_mask", "nms_wmax", "hm_wmax"):
+        a, b = getattr(fast, name).cpu().numpy(), getattr(slow, name).cpu().numpy()
+        if name == "nms_wmax":
+            assert np.array_equal(a, b), f"{name} differs"
+        else:
+            assert np.array_equal(a.view(np.uint32), b.view(np.uint32)), f"{name} differs"
+    # the tag bounds really bound the first tag component of every 4-row x 32-pixel block
+    t0 = fast.agg_tags[..., 0]
+    blk = t0.reshape(B, 17, H // 4, 4, W // 32, 32)
+    lo, hi = blk.amin(dim=(3, 5)), blk.amax(dim=(3, 5))
+    slack = 1e-4 * (1 + lo.abs().max())
+    assert bool((fast.tag_bmin <= lo + slack).all()) and bool((fast.tag_bmax >= hi - slack).all())
