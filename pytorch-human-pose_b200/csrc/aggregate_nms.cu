@@ -543,7 +543,7 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
               a.W >= 256 && a.vec_ok;
     for (int s = 0; ok && s < a.n_scales; ++s) {
       const ScaleDev& S = a.sc[s];
-      ok = S.hh == 2 * S.lh && S.hw == 2 * S.lw && S.lh >= 2 && S.lw >= 4 && S.lw % 4 == 0;
+      ok = S.hh == 2 * S.lh && S.hw == 2 * S.lw && S.lh >= 2 && S.lw >= 4 && S.lw % 4 == 0 && S.hw <= a.W && S.hh <= a.H;
     }
     if (ok) {
       const int NW = a.W >= 512 ? 4 : 2;

@@ -71,7 +71,7 @@ __device__ __forceinline__ void stage_window(float* __restrict__ dst, int dst_st
 }
 
 template <int E, int NW, int NS>
-__global__ void __launch_bounds__(32 * NW) agg_nms_ms_kernel(const AggArgs a, const Geom g) {
+__global__ void __launch_bounds__(32 * NW, 4) agg_nms_ms_kernel(const AggArgs a, const Geom g) {
   extern __shared__ __align__(16) float smem[];
   constexpr int tc = 32 * NW + 8;
   constexpr int nthr = 32 * NW;
@@ -255,19 +255,21 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_ms_kernel(const AggArgs a, co
   int hxa_s[NS];
 #pragma unroll
   for (int s = 0; s < NS; ++s) hxa_s[s] = s_hxa[s];
-  // per-lane column taps of every scale (tile-relative), kept in registers
-  int ci0[NS][4];
-  unsigned cstep[NS];
-  float cw0[NS][4], cw1[NS][4];
+  // per-lane column taps of every scale, kept in registers: tile-relative index of the first column's
+  // left tap, then per column a 2-bit offset to its own left tap (hw <= W, so 4 adjacent output columns
+  // span at most 4 source columns) and 1 bit "right tap = left tap + 1"
+  int cbase[NS];
+  unsigned cpack[NS];
+  float cw1[NS][4];   // w0 is 1 - w1 exactly as axis_tap computes it (recomputed on use)
 #pragma unroll
   for (int s = 0; s < NS; ++s) {
-    cstep[s] = 0;
+    cpack[s] = 0;
 #pragma unroll
     for (int c = 0; c < 4; ++c) {
       const Tap tp = axis_tap(a.sc[s].s_hi_x, min(X0 + c, W - 1), a.sc[s].hw, W);
-      ci0[s][c] = tp.i0 - hxa_s[s];
-      cstep[s] |= (unsigned)(tp.i1 - tp.i0) << c;
-      cw0[s][c] = tp.w0;
+      if (c == 0) cbase[s] = tp.i0 - hxa_s[s];
+      cpack[s] |= (unsigned)(tp.i0 - hxa_s[s] - cbase[s]) << (2 * c);
+      cpack[s] |= (unsigned)(tp.i1 - tp.i0) << (8 + c);
       cw1[s][c] = tp.w1;
     }
   }
@@ -310,9 +312,9 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_ms_kernel(const AggArgs a, co
       const float* sp = smem + g.off_s[s] + r * g.hc[s];
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
-        const int i0 = ci0[s][c];
-        const float v0 = sp[i0], v1 = sp[i0 + ((cstep[s] >> c) & 1u)];
-        h[c] = fmaf(cw0[s][c], v0, __fmul_rn(cw1[s][c], v1));
+        const int i0 = cbase[s] + (int)((cpack[s] >> (2 * c)) & 3u);
+        const float v0 = sp[i0], v1 = sp[i0 + (int)((cpack[s] >> (8 + c)) & 1u)];
+        h[c] = fmaf(1.f - cw1[s][c], v0, __fmul_rn(cw1[s][c], v1));
       }
     };
     float r0[4], r1[4], r2[4], r3[4], vq0[4], vq1[4];

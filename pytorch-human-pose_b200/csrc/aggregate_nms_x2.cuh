@@ -6,18 +6,21 @@
 // including the clamped first/last rows and columns.
 //
 // Work decomposition (B200: issue-bound otherwise -- the generic kernel spends ~370 instructions
-// per output pixel; this one ~30, which leaves the kernel bound by HBM writes):
+// per output pixel; this one ~65, which leaves the kernel bound by HBM writes):
 //   * one CTA = a band of RB output rows x (128 * NW) columns of one (image, joint) plane;
-//   * phase 1 (all threads): flip-averaged quarter-res / half-res tiles and the tag tiles -> smem
-//     (coalesced loads, the flipped operand is read mirrored with the permuted joint index);
-//   * phase 2 (all threads): stage mean S at half resolution, in place, exact torch arithmetic;
+//   * phase 0 (tags first): the tag tiles are staged (16-byte loads, one warp per tile row, the flipped
+//     run read mirrored with the permuted joint index) and every lane writes its 4 columns of all rows
+//     with x4 taps and E-innermost 16-byte stores, plus the per-(4 rows x word) bounds of the first tag
+//     component; the tag tiles alias the half-res tile, so shared memory stays at 30 KB (6 CTAs/SM);
+//   * phase 1 (all threads): flip-averaged quarter-res / half-res tiles -> smem, tile interiors 16-byte
+//     aligned, two rows per batch so that all loads of a batch are in flight before the first store;
+//   * phase 2 (all threads): stage mean S at half resolution, in place, exact torch arithmetic
+//     (compile-time taps for bands that touch neither the first nor the last image rows);
 //   * phase 3 (per warp, no CTA barrier): every lane owns 4 adjacent output columns and walks
 //     down the rows with everything in registers: horizontal interpolation of each half-res row
-//     once (two 8-byte smem loads), vertical interpolation per row, one 16-byte store of the
-//     heatmap, 5-wide row maximum via warp shuffles (halo columns from a per-warp prologue),
-//     5-tall column maximum in a register window, survivor test, and per-32-pixel-word
-//     mask / maxima reduced over the 8 lanes of the word;
-//   * phase 4 (per warp): tags, same walking scheme with x4 taps, E-innermost 16-byte stores.
+//     once, vertical interpolation per row, one 16-byte store of the heatmap, 5-wide row maximum via
+//     warp shuffles (halo columns from a per-warp prologue), 5-tall column maximum in a register
+//     window, survivor test, and per-32-pixel-word mask / maxima reduced over the 8 lanes of the word.
 #pragma once
 
 namespace x2 {
