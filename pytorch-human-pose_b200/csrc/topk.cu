@@ -129,9 +129,24 @@ struct SortedSink {
   // replay only has to feed it this list instead of scanning the row again
   float* log_v;
   int* log_i;
-  int n_log;
+  int n_log, log_cap;
+  float rej_eq;   // merge only: largest value that arrived equal to the then-smallest kept value
+  __device__ __forceinline__ void init_empty() {   // M slots of -inf: the first M arrivals fill them
+    n_log = 0;
+    sv = -INFINITY;
+    si = -1;
+    top = -INFINITY;
+    evicted = -INFINITY;
+    rej_eq = -INFINITY;
+    any_evicted = false;
+  }
+  __device__ __forceinline__ void offer(float cv, int idx) {   // merge step: any value may be offered
+    if (cv > top) insert(cv, idx);
+    else if (cv == top) rej_eq = cv;
+  }
   __device__ __forceinline__ void init(float nv) {
     n_log = 0;
+    rej_eq = -INFINITY;
     sv = lane < M ? nv : -INFINITY;
     si = lane;
     // bitonic sort, descending by value
@@ -157,7 +172,7 @@ struct SortedSink {
     const int ui = __shfl_up_sync(kFull, si, 1);
     evicted = top;
     any_evicted = true;
-    if (lane == 0 && n_log < kLogCap) { log_v[n_log] = cv; log_i[n_log] = idx; }
+    if (lane == 0 && n_log < log_cap) { log_v[n_log] = cv; log_i[n_log] = idx; }
     ++n_log;
     if (lane < M) {
       if (lane > pos) { sv = uv; si = ui; }
@@ -168,7 +183,7 @@ struct SortedSink {
   __device__ __forceinline__ bool ambiguous() const {
     const float nxt = __shfl_down_sync(kFull, sv, 1);
     const bool tie = __ballot_sync(kFull, lane < M - 1 && sv == nxt) != 0u;
-    return tie || (any_evicted && evicted == top);
+    return tie || (any_evicted && evicted == top) || rej_eq == top;
   }
 };
 
@@ -177,19 +192,12 @@ struct SortedSink {
 // entering element are expanded up to 8 at a time so that their heatmap lines and mask words are
 // fetched together instead of one DRAM round trip each.
 template <typename Sink>
-__device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ hm, const uint32_t* __restrict__ mk,
-                                         const float* __restrict__ wm, int H, int W, int wpr, int M, int lane) {
-  {
-    float nv = 0.f;
-    if (lane < M) {
-      const int y = lane / W, x = lane % W;
-      const float v = hm[lane];
-      const bool keep = (mk[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
-      nv = keep ? v : __fmul_rn(v, 0.0f);
-    }
-    sink.init(nv);
-  }
-  const int nwords = H * wpr;
+__device__ __forceinline__ void scan_range(Sink& sink, const float* __restrict__ hm, const uint32_t* __restrict__ mk,
+                                           const float* __restrict__ wm, int W, int wpr, int w_begin, int w_end,
+                                           int first_idx, int lane) {
+  // words [w_begin, w_end) of the row; pixels with flat index < first_idx are not offered (they are the
+  // initial heap of the sequential algorithm)
+  const int nwords = w_end;
   constexpr int kGroup = 4, kSlots = 8, kAhead = 4;
   // word maxima are loaded kAhead groups (of 128 words) ahead of their use
   float ring[kAhead][kGroup];
@@ -197,10 +205,10 @@ __device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ h
   for (int a = 0; a < kAhead; ++a)
 #pragma unroll
     for (int u = 0; u < kGroup; ++u) {
-      const int wd = 32 * (a * kGroup + u) + lane;
+      const int wd = w_begin + 32 * (a * kGroup + u) + lane;
       ring[a][u] = wd < nwords ? wm[wd] : -INFINITY;
     }
-  for (int base = 0; base < nwords; base += 32 * kGroup) {
+  for (int base = w_begin; base < nwords; base += 32 * kGroup) {
     float cur[kGroup];
 #pragma unroll
     for (int u = 0; u < kGroup; ++u) {
@@ -230,7 +238,7 @@ __device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ h
             const int w2 = cbase + l;
             const int y = w2 / wpr, x = (w2 - y * wpr) * 32 + lane;
             const int idx = y * W + x;
-            if (x < W && idx >= M) hv[s] = hm[idx];
+            if (x < W && idx >= first_idx) hv[s] = hm[idx];
             mw[s] = mk[w2];
           }
         }
@@ -240,7 +248,7 @@ __device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ h
           if (!(__shfl_sync(kFull, cur[u], wl[s]) > sink.top)) continue;   // the top may have risen meanwhile
           const int w2 = cbase + wl[s];
           const int y = w2 / wpr, x0 = (w2 - y * wpr) * 32;
-          const bool valid = (x0 + lane < W) && (y * W + x0 + lane >= M);
+          const bool valid = (x0 + lane < W) && (y * W + x0 + lane >= first_idx);
           const bool keep = (mw[s] >> lane) & 1u;
           const float nv = keep ? hv[s] : __fmul_rn(hv[s], 0.0f);
           uint32_t cand = __ballot_sync(kFull, valid && nv > sink.top);
@@ -254,6 +262,26 @@ __device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ h
       }
     }
   }
+}
+
+// NMS'd value of flat element `lane` (the sequential algorithm's initial heap is elements 0..M-1)
+__device__ __forceinline__ float first_element(const float* __restrict__ hm, const uint32_t* __restrict__ mk, int W,
+                                               int wpr, int M, int lane) {
+  float nv = 0.f;
+  if (lane < M) {
+    const int y = lane / W, x = lane % W;
+    const float v = hm[lane];
+    const bool keep = (mk[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
+    nv = keep ? v : __fmul_rn(v, 0.0f);
+  }
+  return nv;
+}
+
+template <typename Sink>
+__device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ hm, const uint32_t* __restrict__ mk,
+                                         const float* __restrict__ wm, int H, int W, int wpr, int M, int lane) {
+  sink.init(first_element(hm, mk, W, wpr, M, lane));
+  scan_range(sink, hm, mk, wm, W, wpr, 0, H * wpr, M, lane);
 }
 
 __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __restrict__ agg_hm,
@@ -283,7 +311,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __re
   if (!force_exact) {
     SortedSink fast;
     fast.M = M; fast.lane = lane;
-    fast.log_v = s_logv[warp]; fast.log_i = s_logi[warp];
+    fast.log_v = s_logv[warp]; fast.log_i = s_logi[warp]; fast.log_cap = kLogCap;
     scan_row(fast, hm, mk, wm, H, W, wpr, M, lane);
     if (!fast.ambiguous()) { out_v = fast.sv; out_i = fast.si; done = true; }
     else n_logged = fast.n_log;
@@ -294,17 +322,115 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __re
     exact.M = M; exact.lane = lane;
     if (n_logged >= 0 && n_logged <= kLogCap) {
       // same entering elements, same order: build the heap from the first M elements and feed the log
-      float nv = 0.f;
-      if (lane < M) {
-        const int y = lane / W, x = lane % W;
-        const float v = hm[lane];
-        const bool keep = (mk[(size_t)y * wpr + (x >> 5)] >> (x & 31)) & 1u;
-        nv = keep ? v : __fmul_rn(v, 0.0f);
-      }
-      exact.init(nv);
+      exact.init(first_element(hm, mk, W, wpr, M, lane));
       __syncwarp();
       if (lane == 0)
         for (int i = 0; i < n_logged; ++i) adjust_heap(exact.h, 0, M, s_logv[warp][i], s_logi[warp][i]);
+    } else {
+      scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
+    }
+    __syncwarp();
+    if (lane == 0) sort_heap(exact.h, M);
+    __syncwarp();
+    if (lane < M) { out_v = exact.h.v[lane]; out_i = exact.h.i[lane]; }
+  }
+  if (lane < M) {
+    const size_t o = (size_t)row * M + lane;
+    scores_k[o] = out_v;
+    idx_k[o] = out_i;
+    coords_k[o * 2 + 0] = out_i % W;
+    coords_k[o * 2 + 1] = out_i / W;
+    for (int e = 0; e < E; ++e) tags_k[o * E + e] = agg_tags[((size_t)row * H * W + out_i) * E + e];
+  }
+}
+
+// Small batches: kSplitWarps warps per (image, joint) row.  Every warp streams one contiguous segment of
+// the row through its own sorted sink, started empty (a segment's smallest kept value never exceeds the
+// sequential algorithm's at the same position, so the segment keeps and logs a superset of what enters
+// there); warp 0 merges the segment lists.  The merged top M is final iff it is free of ties (no equal
+// values among the top M, no other listed element equal to the M-th value, no segment evicted an element
+// equal to it); otherwise warp 0 replays the concatenated segment logs, which are in index order, through
+// the exact libstdc++ heap.
+constexpr int kSplitWarps = 8;
+constexpr int kSegLogCap = 320;
+
+__global__ void __launch_bounds__(kSplitWarps * 32) topk_split_kernel(const float* __restrict__ agg_hm,
+                                                                     const float* __restrict__ agg_tags,
+                                                                     const uint32_t* __restrict__ mask,
+                                                                     const float* __restrict__ wmax, int H, int W,
+                                                                     int wpr, int E, int M, int force_exact,
+                                                                     float* __restrict__ scores_k,
+                                                                     int32_t* __restrict__ idx_k,
+                                                                     int32_t* __restrict__ coords_k,
+                                                                     float* __restrict__ tags_k) {
+  __shared__ float s_v[kSplitWarps][32];
+  __shared__ int s_i[kSplitWarps][32];
+  __shared__ float s_logv[kSplitWarps][kSegLogCap];
+  __shared__ int s_logi[kSplitWarps][kSegLogCap];
+  __shared__ float s_evicted[kSplitWarps];
+  __shared__ int s_nlog[kSplitWarps];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int row = blockIdx.x;
+  const float* hm = agg_hm + (size_t)row * H * W;
+  const uint32_t* mk = mask + (size_t)row * H * wpr;
+  const float* wm = wmax + (size_t)row * H * wpr;
+  const int nwords = H * wpr;
+
+  if (!force_exact) {
+    const int groups = (nwords + 127) / 128;   // segment bounds in whole groups of 128 words
+    const int gb = (groups * warp) / kSplitWarps, ge = (groups * (warp + 1)) / kSplitWarps;
+    SortedSink seg;
+    seg.M = M; seg.lane = lane;
+    seg.log_v = s_logv[warp]; seg.log_i = s_logi[warp]; seg.log_cap = kSegLogCap;
+    seg.init_empty();
+    scan_range(seg, hm, mk, wm, W, wpr, gb * 128, min(ge * 128, nwords), 0, lane);
+    s_v[warp][lane] = seg.sv;
+    s_i[warp][lane] = seg.si;
+    if (lane == 0) {
+      s_evicted[warp] = seg.any_evicted ? seg.evicted : -INFINITY;
+      s_nlog[warp] = seg.n_log;
+    }
+  }
+  __syncthreads();
+  if (warp != 0) return;
+
+  float out_v = 0.f;
+  int out_i = 0;
+  bool done = false, logs_ok = !force_exact;
+  if (!force_exact) {
+    SortedSink all;
+    all.M = M; all.lane = lane;
+    all.log_v = nullptr; all.log_i = nullptr; all.log_cap = 0;
+    all.init_empty();
+    for (int w = 0; w < kSplitWarps; ++w) {
+      const float cvl = s_v[w][lane];
+      const int cil = s_i[w][lane];
+      for (int j = 0; j < M; ++j) {           // descending: stop at the first value that cannot matter
+        const float cv = __shfl_sync(kFull, cvl, j);
+        if (cv < all.top || cv == -INFINITY) break;
+        all.offer(cv, __shfl_sync(kFull, cil, j));
+      }
+      logs_ok = logs_ok && s_nlog[w] <= kSegLogCap;
+    }
+    bool amb = all.ambiguous();
+    for (int w = 0; w < kSplitWarps; ++w) amb = amb || (s_evicted[w] == all.top);
+    if (!amb) { out_v = all.sv; out_i = all.si; done = true; }
+  }
+  if (!done) {
+    HeapSink exact;
+    exact.h = HeapRef{s_v[0], s_i[0]};
+    exact.M = M; exact.lane = lane;
+    if (logs_ok) {
+      exact.init(first_element(hm, mk, W, wpr, M, lane));
+      __syncwarp();
+      if (lane == 0) {
+        for (int w = 0; w < kSplitWarps; ++w)
+          for (int i = 0; i < s_nlog[w]; ++i) {
+            const float cv = s_logv[w][i];
+            const int ci = s_logi[w][i];
+            if (ci >= M && cv > exact.h.v[0]) adjust_heap(exact.h, 0, M, cv, ci);
+          }
+      }
     } else {
       scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
     }
@@ -333,9 +459,16 @@ int launch_topk(const HpdParams* p, const HpdBuffers* buf, cudaStream_t st) {
   }
   const int rows = p->batch * p->num_kpts;
   const int wpr = (p->out_w + 31) / 32;
-  topk_kernel<<<(rows + kTopkWarps - 1) / kTopkWarps, kTopkWarps * 32, 0, st>>>(
-      buf->agg_hm, buf->agg_tags, buf->nms_mask, buf->nms_wmax, rows, p->out_h, p->out_w, wpr, p->emb, p->max_people,
-      p->force_generic, buf->scores_k, buf->idx_k, buf->coords_k, buf->tags_k);
+  // small batches: kSplitWarps warps per row cut the per-row latency; large ones fill the GPU with one warp per row
+  const bool split = rows <= 512 && (long long)p->out_h * wpr >= 128 * kSplitWarps && !(p->force_generic & 2);
+  if (split)
+    topk_split_kernel<<<rows, kSplitWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->nms_mask, buf->nms_wmax, p->out_h,
+                                                         p->out_w, wpr, p->emb, p->max_people, p->force_generic & 1,
+                                                         buf->scores_k, buf->idx_k, buf->coords_k, buf->tags_k);
+  else
+    topk_kernel<<<(rows + kTopkWarps - 1) / kTopkWarps, kTopkWarps * 32, 0, st>>>(
+        buf->agg_hm, buf->agg_tags, buf->nms_mask, buf->nms_wmax, rows, p->out_h, p->out_w, wpr, p->emb, p->max_people,
+        p->force_generic & 1, buf->scores_k, buf->idx_k, buf->coords_k, buf->tags_k);
   count_launch();
   return check_launch("topk_kernel");
 }
