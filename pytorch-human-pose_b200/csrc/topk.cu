@@ -423,13 +423,28 @@ __global__ void __launch_bounds__(kSplitWarps * 32) topk_split_kernel(const floa
     if (logs_ok) {
       exact.init(first_element(hm, mk, W, wpr, M, lane));
       __syncwarp();
-      if (lane == 0) {
-        for (int w = 0; w < kSplitWarps; ++w)
-          for (int i = 0; i < s_nlog[w]; ++i) {
-            const float cv = s_logv[w][i];
-            const int ci = s_logi[w][i];
-            if (ci >= M && cv > exact.h.v[0]) adjust_heap(exact.h, 0, M, cv, ci);
+      // the logs hold a superset of the entering elements in index order: filter 32 entries at a time
+      // against the live top, replay the survivors one by one
+      float top = exact.top;
+      for (int w = 0; w < kSplitWarps; ++w) {
+        const int n = s_nlog[w];
+        for (int i0 = 0; i0 < n; i0 += 32) {
+          const int i = i0 + lane;
+          const float cv = i < n ? s_logv[w][i] : -INFINITY;
+          const int ci = i < n ? s_logi[w][i] : 0;
+          uint32_t pass = __ballot_sync(kFull, i < n && ci >= M && cv > top);
+          while (pass) {
+            const int j = __ffs(pass) - 1;
+            pass &= pass - 1;
+            const float cvj = __shfl_sync(kFull, cv, j);
+            const int cij = __shfl_sync(kFull, ci, j);
+            if (cvj > top) {
+              if (lane == 0) adjust_heap(exact.h, 0, M, cvj, cij);
+              __syncwarp();
+              top = exact.h.v[0];
+            }
           }
+        }
       }
     } else {
       scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
