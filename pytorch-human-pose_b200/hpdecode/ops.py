@@ -99,6 +99,25 @@ class DecodeBuffers:
         self.flags = torch.empty((B,), **i32)
         self.workspace = None
 
+    @classmethod
+    def for_grouping(cls, scores_k: Tensor, coords_k: Tensor, tags_k: Tensor) -> "DecodeBuffers":
+        """Only what hpd_group touches (top-k inputs, pose outputs); the map-sized buffers stay empty."""
+        B, K, M, E = tags_k.shape
+        dev = tags_k.device
+        self = cls.__new__(cls)
+        self.shape = (B, K, 0, 0, E, M)
+        zf = torch.empty((0,), device=dev, dtype=torch.float32)
+        zi = torch.empty((0,), device=dev, dtype=torch.int32)
+        self.agg_hm = self.agg_tags = self.nms_wmax = self.hm_wmax = self.tag_bmin = self.tag_bmax = zf
+        self.person_scores = zf
+        self.nms_mask = self.idx_k = zi
+        self.scores_k, self.coords_k, self.tags_k = scores_k, coords_k, tags_k
+        self.poses = torch.empty((B, M, K, 3 + E), device=dev, dtype=torch.float32)
+        self.n_person = torch.empty((B,), device=dev, dtype=torch.int32)
+        self.flags = torch.empty((B,), device=dev, dtype=torch.int32)
+        self.workspace = None
+        return self
+
     def struct(self) -> HpdBuffers:
         s = HpdBuffers()
         for name, _ in HpdBuffers._fields_:
@@ -265,16 +284,8 @@ def group_op(tags_k: Tensor, coords_k: Tensor, scores_k: Tensor, det_thr: float,
     _require_cuda(scores_k, "scores_k")
     B, K, M, E = tags_k.shape
     dev = tags_k.device
-    bufs = DecodeBuffers.__new__(DecodeBuffers)
     params = make_params(B, K, out_h, out_w, E, M, det_thr, tag_thr)
-    z = torch.empty((0,), device=dev)
-    bufs.agg_hm = bufs.agg_tags = bufs.nms_wmax = bufs.hm_wmax = bufs.person_scores = bufs.tag_bmin = bufs.tag_bmax = z
-    bufs.nms_mask = bufs.idx_k = torch.empty((0,), device=dev, dtype=torch.int32)
-    bufs.scores_k, bufs.coords_k, bufs.tags_k = scores_k.contiguous(), coords_k.contiguous().int(), tags_k.contiguous()
-    bufs.poses = torch.empty((B, M, K, 3 + E), device=dev, dtype=torch.float32)
-    bufs.n_person = torch.empty((B,), device=dev, dtype=torch.int32)
-    bufs.flags = torch.empty((B,), device=dev, dtype=torch.int32)
-    bufs.workspace = None
+    bufs = DecodeBuffers.for_grouping(scores_k.contiguous(), coords_k.contiguous().int(), tags_k.contiguous())
     run_stage("group", bufs, params)
     return [bufs.poses, bufs.n_person, bufs.flags]
 

@@ -179,3 +179,20 @@ def test_nonsquare_other_joint_count_and_m20(oracle):
         else:
             assert np.array_equal(_bits(out[b][0]), _bits(ref["grouped_joints"]))
             assert np.array_equal(_bits(out[b][1]), _bits(ref["person_scores"]))
+
+
+@pytest.mark.parametrize("M", [5, 32])
+def test_extreme_max_people(M, oracle):
+    """max_num_people at its smallest sensible value and at the library's limit (32 = warp width)."""
+    from hpdecode import BottomUpDecoder
+    scales = synth.crowd(2, 256, persons=28, flip=True, seed=90 + M, tag_spread=1.1)
+    dec = BottomUpDecoder(17, M, 0.05, 0.5, "cuda:0")
+    res = dec.decode(_dev(scales), (256, 256))
+    out = res.to_numpy()
+    for b in range(2):
+        hm_o, tg_o = oracle.aggregate(synth.image_slice(scales, b), (256, 256))
+        ref = oracle.parse(hm_o, tg_o, M, 0.05, 0.5)
+        assert np.array_equal(res.bufs.idx_k[b].cpu().numpy(), ref["idx_k"])
+        assert out[b][0].shape == ref["grouped_joints"].shape
+        assert np.array_equal(_bits(out[b][0]), _bits(ref["grouped_joints"]))
+        assert np.array_equal(_bits(out[b][1]), _bits(ref["person_scores"]))
