@@ -333,8 +333,8 @@ def run_ours(args):
                          "timing": "CUDA events around each of the K launches, one batch in flight"},
             "stage_ms": dict(zip(stages, stage_ms)), "sequential_ms_per_step": seq_ms, "streams": NS,
             "grouping": {"kernel_ms": stage_ms[2], "latency_us_per_image": 1e3 * stage_ms[2],
-                         "amortised_us_per_image": 1e3 * stage_ms[2] / B, "resident_warps": B,
-                         "sm_occupancy_pct": 100.0 * B / (torch.cuda.get_device_properties(dev).multi_processor_count * 64),
+                         "amortised_us_per_image": 1e3 * stage_ms[2] / B, "resident_warps": 4 * B,
+                         "sm_occupancy_pct": 100.0 * 4 * B / (torch.cuda.get_device_properties(dev).multi_processor_count * 64),
                          "note": "one warp per image; all images of a batch run concurrently, so the kernel duration is "
                                  "each image's latency"},
             "persons_per_image": float(n_person.mean()),

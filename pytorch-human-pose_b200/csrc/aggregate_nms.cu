@@ -18,6 +18,9 @@
 // This file holds the GENERIC kernel (any resize ratios, any number of scales).  It is the
 // correctness anchor; aggregate_nms_x2.cu specialises the standard single-scale x2/x2/x4 case.
 #include "common.cuh"
+#ifdef HPD_MS_PROFILE
+#include <cstdio>
+#endif
 
 namespace hpd {
 
@@ -546,7 +549,13 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
       ok = S.hh == 2 * S.lh && S.hw == 2 * S.lw && S.lh >= 2 && S.lw >= 4 && S.lw % 4 == 0 && S.hw <= a.W && S.hh <= a.H;
     }
     if (ok) {
-      const int NW = a.W >= 512 ? 4 : 2;
+      // warps (128-column strips) per CTA: the count in 2..5 that pads the row least, the larger on ties
+      // (640 columns: 5 -- one CTA per band with every warp busy; 4 would leave 3 of 8 strips empty)
+      int NW = 2;
+      for (int c = 3; c <= 5; ++c) {
+        const int pad_c = (a.W + 128 * c - 1) / (128 * c) * c, pad_n = (a.W + 128 * NW - 1) / (128 * NW) * NW;
+        if (pad_c <= pad_n) NW = c;
+      }
       ms::Geom g;
       memset(&g, 0, sizeof(g));
       int off = 0;
@@ -559,18 +568,18 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
         g.hr[s] = hr;
         g.hc[s] = (hc + 6 + 3) & ~3;      // origin rounded down / width rounded up to 4 in the kernel
         off += g.hr[s] * g.hc[s];
-        g.lr = lr > g.lr ? lr : g.lr;
-        lc = (lc + 6 + 3) & ~3;
-        g.lc = lc > g.lc ? lc : g.lc;
-        g.hr_max = hr > g.hr_max ? hr : g.hr_max;
+        g.lr[s] = lr;
+        g.lc[s] = (lc + 6 + 3) & ~3;
       }
       const int tag_words = a.E * ms::TR * (32 * NW + 8);
       off = off > tag_words ? off : tag_words;
       off = (off + 3) & ~3;
-      g.off_lo = off;   off += (g.lr * g.lc + 3) & ~3;
+      for (int s = 0; s < a.n_scales; ++s) {
+        g.off_lo[s] = off;
+        off += (g.lr[s] * g.lc[s] + 3) & ~3;
+      }
       g.off_edge = off; off += NW * ms::NROWS * 4;
-      g.off_tab = off;  off += 4 * a.n_scales * ms::NROWS;
-      g.off_rt2 = off;  off += 4 * g.hr_max;
+      g.off_tab = off;  off += 3 * a.n_scales * ms::NROWS;
       g.total = off;
       const size_t smem = sizeof(float) * (size_t)g.total;
       if (smem <= 200 * 1024) {
@@ -585,8 +594,8 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
   do {                                                                                                           \
     if (a.n_scales == 1) HPD_MS_LAUNCH(E_, NW_, 1); else if (a.n_scales == 2) HPD_MS_LAUNCH(E_, NW_, 2); else HPD_MS_LAUNCH(E_, NW_, 3); \
   } while (0)
-        if (a.E == 1) { if (NW == 4) HPD_MS_NS(1, 4); else HPD_MS_NS(1, 2); }
-        else          { if (NW == 4) HPD_MS_NS(2, 4); else HPD_MS_NS(2, 2); }
+        if (a.E == 1) { if (NW == 5) HPD_MS_NS(1, 5); else if (NW == 4) HPD_MS_NS(1, 4); else if (NW == 3) HPD_MS_NS(1, 3); else HPD_MS_NS(1, 2); }
+        else          { if (NW == 5) HPD_MS_NS(2, 5); else if (NW == 4) HPD_MS_NS(2, 4); else if (NW == 3) HPD_MS_NS(2, 3); else HPD_MS_NS(2, 2); }
 #undef HPD_MS_NS
 #undef HPD_MS_LAUNCH
         count_launch();

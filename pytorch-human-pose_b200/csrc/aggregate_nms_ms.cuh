@@ -15,6 +15,13 @@
 
 namespace ms {
 
+// -DHPD_MS_PROFILE: one CTA in the middle of the grid prints clock64() per phase (development aid)
+#ifdef HPD_MS_PROFILE
+#define MSP_MARK(i) do { if (prof) pt[i] = clock64(); } while (0)
+#else
+#define MSP_MARK(i)
+#endif
+
 using x2::clampi;
 using x2::max3;
 using x2::tap_x2;
@@ -25,69 +32,105 @@ constexpr int TR = RB / 4 + 2;    // quarter-res tag rows staged
 
 struct Geom {                     // shared-memory layout, computed on the host
   int off_s[HPD_MAX_SCALES];      // float offset of S_s
-  int hr[HPD_MAX_SCALES], hc[HPD_MAX_SCALES];   // rows / (even) row stride of S_s
-  int off_lo, lr, lc;             // quarter-res staging tile (shared by the scales)
-  int off_edge, off_tab, off_rt2, off_ninf, total;
-  int hr_max;
+  int hr[HPD_MAX_SCALES], hc[HPD_MAX_SCALES];   // rows / row stride (multiple of 4) of S_s
+  int off_lo[HPD_MAX_SCALES];     // quarter-res staging tile of scale s
+  int lr[HPD_MAX_SCALES], lc[HPD_MAX_SCALES];
+  int off_edge, off_tab, total;
 };
 
-// Stage an in-image window of nrows x (4 * nvec) columns starting at the 4-aligned column xa into shared
-// memory (row stride a multiple of 4): one warp per row, 16-byte loads (the flipped operand as the mirrored
-// 16 bytes, reversed in registers), all loads of a row in flight before the first store.
-template <int NW>
-__device__ __forceinline__ void stage_window(float* __restrict__ dst, int dst_stride, const float* __restrict__ p,
-                                             const float* __restrict__ pf, int ya, int xa, int nrows, int nvec,
-                                             int w, int warp, int lane) {
+// One staged window (a scale's quarter- or half-res rows).  Row r of it is the job "copy nvec 16-byte
+// vectors from p + r*w, flip-averaged with the vectors running backwards from pf + r*w, to
+// smem[dst + r*stride]".
+struct Seg {
+  const float* p;                 // first vector of row 0
+  const float* pf;                // mirrored first vector of row 0 in the flipped run's map, or null
+  int dst, stride, nvec, w, rows;
+};
+
+// Stage all windows: the rows of all segments form one job list dealt round-robin to the warps; a warp
+// keeps two rows in flight (all loads of both issued before the first store).  16-byte loads; the flipped
+// operand is read as the mirrored 16 bytes and reversed in registers (model.py:87-90).
+template <int NW, int NSEG>
+__device__ __forceinline__ void stage_segments(float* __restrict__ smem, const Seg* __restrict__ seg, int warp, int lane) {
   constexpr int MAXIT = 4;
-  for (int r = warp; r < nrows; r += NW) {
-    const int rowo = (ya + r) * w;
-    for (int qb = 0; qb < nvec; qb += 32 * MAXIT) {
-      float4 v[MAXIT], f[MAXIT];
+  int start[NSEG + 1];
+  start[0] = 0;
 #pragma unroll
-      for (int u = 0; u < MAXIT; ++u) {
-        const int q = qb + lane + 32 * u;
-        if (q < nvec) {
-          const int x = xa + 4 * q;
-          v[u] = __ldg(reinterpret_cast<const float4*>(p + rowo + x));
-          if (pf) f[u] = __ldg(reinterpret_cast<const float4*>(pf + rowo + (w - 4 - x)));
-        }
-      }
+  for (int i = 0; i < NSEG; ++i) start[i + 1] = start[i] + seg[i].rows;
+  const int njobs = start[NSEG];
+  struct Row { const float* p; const float* pf; float* dst; int nvec; };
+  auto locate = [&](int j) {
+    Row r{nullptr, nullptr, nullptr, 0};
+    if (j < njobs) {
+      int sg = 0, first = 0;
 #pragma unroll
-      for (int u = 0; u < MAXIT; ++u) {
-        const int q = qb + lane + 32 * u;
-        if (q < nvec) {
-          float4 o = v[u];
-          if (pf) {
-            o.x = __fmul_rn(__fadd_rn(v[u].x, f[u].w), 0.5f);
-            o.y = __fmul_rn(__fadd_rn(v[u].y, f[u].z), 0.5f);
-            o.z = __fmul_rn(__fadd_rn(v[u].z, f[u].y), 0.5f);
-            o.w = __fmul_rn(__fadd_rn(v[u].w, f[u].x), 0.5f);
-          }
-          *reinterpret_cast<float4*>(dst + r * dst_stride + 4 * q) = o;
-        }
+      for (int i = 1; i < NSEG; ++i)
+        if (j >= start[i]) { sg = i; first = start[i]; }
+      const Seg& S = seg[sg];
+      const int rr = j - first;
+      r.p = S.p + (size_t)rr * S.w;
+      r.pf = S.pf ? S.pf + (size_t)rr * S.w : nullptr;
+      r.dst = smem + S.dst + rr * S.stride;
+      r.nvec = S.nvec;
+    }
+    return r;
+  };
+  // (the "whole group of 32 vectors is past the row" tests are warp-uniform: real branches, so short
+  // rows do not pay for MAXIT predicated-off copies)
+  auto load = [&](const Row& r, int qb, float4 (&v)[MAXIT], float4 (&f)[MAXIT]) {
+#pragma unroll
+    for (int u = 0; u < MAXIT; ++u) {
+      if (qb + 32 * u >= r.nvec) break;
+      const int q = qb + lane + 32 * u;
+      if (q < r.nvec) {
+        v[u] = __ldg(reinterpret_cast<const float4*>(r.p) + q);
+        if (r.pf) f[u] = __ldg(reinterpret_cast<const float4*>(r.pf) - q);
       }
+    }
+  };
+  auto store = [&](const Row& r, int qb, const float4 (&v)[MAXIT], const float4 (&f)[MAXIT]) {
+#pragma unroll
+    for (int u = 0; u < MAXIT; ++u) {
+      if (qb + 32 * u >= r.nvec) break;
+      const int q = qb + lane + 32 * u;
+      if (q < r.nvec) {
+        float4 o = v[u];
+        if (r.pf) {
+          o.x = __fmul_rn(__fadd_rn(v[u].x, f[u].w), 0.5f);
+          o.y = __fmul_rn(__fadd_rn(v[u].y, f[u].z), 0.5f);
+          o.z = __fmul_rn(__fadd_rn(v[u].z, f[u].y), 0.5f);
+          o.w = __fmul_rn(__fadd_rn(v[u].w, f[u].x), 0.5f);
+        }
+        reinterpret_cast<float4*>(r.dst)[q] = o;
+      }
+    }
+  };
+  for (int j = warp; j < njobs; j += 2 * NW) {
+    const Row A = locate(j), B = locate(j + NW);
+    const int nv = max(A.nvec, B.nvec);
+    for (int qb = 0; qb < nv; qb += 32 * MAXIT) {
+      float4 va[MAXIT], fa[MAXIT], vb[MAXIT], fb[MAXIT];
+      load(A, qb, va, fa);
+      load(B, qb, vb, fb);
+      store(A, qb, va, fa);
+      store(B, qb, vb, fb);
     }
   }
 }
 
 template <int E, int NW, int NS>
-__global__ void __launch_bounds__(32 * NW, 4) agg_nms_ms_kernel(const AggArgs a, const Geom g) {
+__global__ void __launch_bounds__(32 * NW, 16 / NW) agg_nms_ms_kernel(const AggArgs a, const Geom g) {
   extern __shared__ __align__(16) float smem[];
   constexpr int tc = 32 * NW + 8;
   constexpr int nthr = 32 * NW;
   float* sT = smem;                                   // tags alias the S tiles (consumed first)
-  float* sLo = smem + g.off_lo;
   float* sEdge = smem + g.off_edge;
-  // out-row -> S_s row taps: [NS][NROWS] x (i0, i1, w0, w1)
-  int* rt_i0 = (int*)(smem + g.off_tab);
-  int* rt_i1 = rt_i0 + NS * NROWS;
-  float* rt_w0 = (float*)(rt_i1 + NS * NROWS);
+  // out-row -> S_s row taps: [NS][NROWS] x (packed i0 | i1 << 8 | advance << 16, w0, w1); the advance code
+  // says how the walk's two cached rows move on: 0 keep both, 1 shift (new i0 = old i1), 2 reload; -1 = the
+  // output row is outside the image
+  int* rt_pk = (int*)(smem + g.off_tab);
+  float* rt_w0 = (float*)(rt_pk + NS * NROWS);
   float* rt_w1 = rt_w0 + NS * NROWS;
-  // phase 2 taps: S_s row -> lo tile rows, [hr_max] x (i0, i1, w0, w1)
-  int* p2_i0 = (int*)(smem + g.off_rt2);
-  int* p2_i1 = p2_i0 + g.hr_max;
-  float* p2_w0 = (float*)(p2_i1 + g.hr_max);
-  float* p2_w1 = p2_w0 + g.hr_max;
 
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int bk = blockIdx.z, b = bk / a.K, k = bk % a.K, kf = a.flip[k];
@@ -98,6 +141,44 @@ __global__ void __launch_bounds__(32 * NW, 4) agg_nms_ms_kernel(const AggArgs a,
   const bool active = X0 < W;
   const int ys = y0 - 2;
   const float NINF = -INFINITY;
+#ifdef HPD_MS_PROFILE
+  const bool prof = tid == 0 && blockIdx.x == 0 && blockIdx.y == gridDim.y / 2 && blockIdx.z == gridDim.z / 2;
+  long long pt[8];
+#endif
+  MSP_MARK(0);
+
+  // windows of every scale this CTA needs (hya, hxa, nhy, nhx, lya, lxa) and the staging jobs for them;
+  // published by the first barrier of phase 0
+  __shared__ int s_win[HPD_MAX_SCALES][6];
+  __shared__ Seg s_seg[2 * HPD_MAX_SCALES];
+  if (tid < NS) {
+    const int s = tid;
+    const ScaleDev& S = a.sc[s];
+    const int oya = max(y0 - 2, 0), oyb = min(y0 + RB + 2, H) - 1;
+    const int oxa = max(x0 - 2, 0), oxb = min(x0 + 128 * NW + 2, W) - 1;
+    const int hya = axis_tap(S.s_hi_y, oya, S.hh, H).i0, hyb = axis_tap(S.s_hi_y, oyb, S.hh, H).i1;
+    // column origins are rounded down to a multiple of 4 and widths up, so that rows move as 16-byte vectors
+    const int hxa = axis_tap(S.s_hi_x, oxa, S.hw, W).i0 & ~3, hxb = axis_tap(S.s_hi_x, oxb, S.hw, W).i1 | 3;
+    const int nhy = hyb - hya + 1, nhx = min(hxb, S.hw - 1) - hxa + 1;
+    int t0, t1; float tw0, tw1;
+    tap_x2(hya, S.lh, t0, t1, tw0, tw1);
+    const int lya = t0;
+    tap_x2(hyb, S.lh, t0, t1, tw0, tw1);
+    const int nly = t1 - lya + 1;
+    tap_x2(hxa, S.lw, t0, t1, tw0, tw1);
+    const int lxa = t0 & ~3;
+    tap_x2(min(hxb, S.hw - 1), S.lw, t0, t1, tw0, tw1);
+    const int nlx = min(t1 | 3, S.lw - 1) - lxa + 1;
+    s_win[s][0] = hya; s_win[s][1] = hxa; s_win[s][2] = nhy; s_win[s][3] = nhx; s_win[s][4] = lya; s_win[s][5] = lxa;
+    Seg& lo = s_seg[2 * s];
+    Seg& hi = s_seg[2 * s + 1];
+    lo.p = S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc + (size_t)lya * S.lw + lxa;
+    lo.pf = S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc + (size_t)lya * S.lw + (S.lw - 4 - lxa) : nullptr;
+    lo.dst = g.off_lo[s]; lo.stride = g.lc[s]; lo.nvec = nlx >> 2; lo.w = S.lw; lo.rows = nly;
+    hi.p = S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc + (size_t)hya * S.hw + hxa;
+    hi.pf = S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc + (size_t)hya * S.hw + (S.hw - 4 - hxa) : nullptr;
+    hi.dst = g.off_s[s]; hi.stride = g.hc[s]; hi.nvec = nhx >> 2; hi.w = S.hw; hi.rows = nhy;
+  }
 
   // ---------------- phase 0: tags (x4), identical to the x2 kernel ------------------------------------
   {
@@ -191,70 +272,72 @@ __global__ void __launch_bounds__(32 * NW, 4) agg_nms_ms_kernel(const AggArgs a,
     __syncthreads();
   }
 
-  // ---------------- phases 1+2 per scale: S_s = (up2(avg lo) + avg hi) * 0.5 in shared memory ------------
-  const int oya = max(y0 - 2, 0), oyb = min(y0 + RB + 2, H) - 1;
-  const int oxa = max(x0 - 2, 0), oxb = min(x0 + 128 * NW + 2, W) - 1;
-  // (a real loop over the scales: the body is large and runs once per CTA -- unrolling it only thrashes
-  // the instruction cache)
-  __shared__ int s_hxa[HPD_MAX_SCALES];
+  MSP_MARK(1);
+  // ---------------- phase 1: flip-averaged quarter- and half-res windows of every scale -> smem ---------
+  // (s_seg / s_win were filled at kernel entry; the barrier that ended phase 0 published them)
+  stage_segments<NW, 2 * NS>(smem, s_seg, warp, lane);
+  for (int i = tid; i < NS * NROWS; i += nthr) {     // output row -> S_s rows
+    const int s = i / NROWS, t = i - s * NROWS;
+    const ScaleDev& S = a.sc[s];
+    const int hya = s_win[s][0];
+    const int y = ys + t;
+    int pk = -1;
+    if (y >= 0 && y < H) {
+      const Tap tp = axis_tap(S.s_hi_y, y, S.hh, H);
+      int adv = 2;
+      if (t > 0 && y > 0) {
+        const Tap pv = axis_tap(S.s_hi_y, y - 1, S.hh, H);
+        adv = (pv.i0 == tp.i0 && pv.i1 == tp.i1) ? 0 : ((pv.i1 == tp.i0) ? 1 : 2);
+      }
+      pk = (tp.i0 - hya) | ((tp.i1 - hya) << 8) | (adv << 16);
+      rt_w0[i] = tp.w0; rt_w1[i] = tp.w1;
+    }
+    rt_pk[i] = pk;
+  }
+  __syncthreads();
+  // ---------------- phase 2: S_s = (up2(lo_s) + hi_s) * 0.5 in place (results.py:225-226) -----------------
+  // One item = 4 adjacent half-res columns C..C+3 (C a multiple of 4) of one row: their x2 taps touch the
+  // quarter-res columns C/2-1 .. C/2+2, loaded once per row as scalar + aligned pair + scalar.
+  // (a real loop over the scales: unrolling the body only thrashes the instruction cache)
 #pragma unroll 1
   for (int s = 0; s < NS; ++s) {
     const ScaleDev& S = a.sc[s];
     float* sS = smem + g.off_s[s];
-    const int hc = g.hc[s];
-    const int hya = axis_tap(S.s_hi_y, oya, S.hh, H).i0, hyb = axis_tap(S.s_hi_y, oyb, S.hh, H).i1;
-    // column origins are rounded down to a multiple of 4 and widths up, so that rows move as 16-byte vectors
-    const int hxa = axis_tap(S.s_hi_x, oxa, S.hw, W).i0 & ~3, hxb = axis_tap(S.s_hi_x, oxb, S.hw, W).i1 | 3;
-    if (tid == 0) s_hxa[s] = hxa;
-    const int nhy = hyb - hya + 1, nhx = min(hxb, S.hw - 1) - hxa + 1;
-    int t0, t1; float tw0, tw1;
-    tap_x2(hya, S.lh, t0, t1, tw0, tw1);
-    const int lya = t0;
-    tap_x2(hyb, S.lh, t0, t1, tw0, tw1);
-    const int nly = t1 - lya + 1;
-    tap_x2(hxa, S.lw, t0, t1, tw0, tw1);
-    const int lxa = t0 & ~3;
-    tap_x2(min(hxb, S.hw - 1), S.lw, t0, t1, tw0, tw1);
-    const int nlx = min(t1 | 3, S.lw - 1) - lxa + 1;
-    stage_window<NW>(sLo, g.lc, S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc,
-                     S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr, lya, lxa, nly, nlx >> 2,
-                     S.lw, warp, lane);
-    stage_window<NW>(sS, hc, S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc,
-                     S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr, hya, hxa, nhy, nhx >> 2,
-                     S.hw, warp, lane);
-    for (int r = tid; r < nhy; r += nthr) {       // S_s row -> lo tile rows
-      int i0, i1; float w0, w1;
-      tap_x2(hya + r, S.lh, i0, i1, w0, w1);
-      p2_i0[r] = i0 - lya; p2_i1[r] = i1 - lya; p2_w0[r] = w0; p2_w1[r] = w1;
+    const float* sLo = smem + g.off_lo[s];
+    const int hc = g.hc[s], lc = g.lc[s];
+    const int hya = s_win[s][0], hxa = s_win[s][1], nhy = s_win[s][2], nhx = s_win[s][3], lya = s_win[s][4], lxa = s_win[s][5];
+    const int nq = nhx >> 2, nit = nq * nhy;
+    const unsigned inv = 0xffffffffu / (unsigned)nq + 1u;     // idx / nq == umulhi(idx, inv) for idx * nq < 2^32
+    for (int idx = tid; idx < nit; idx += nthr) {
+      const int r = (int)__umulhi((unsigned)idx, inv), c4 = idx - r * nq;
+      const int C = hxa + 4 * c4, j = C >> 1, jj = j - lxa;
+      int i0, i1; float wy0, wy1;
+      tap_x2(hya + r, S.lh, i0, i1, wy0, wy1);
+      const float* r0 = sLo + (i0 - lya) * lc + jj;
+      const float* r1 = sLo + (i1 - lya) * lc + jj;
+      const int dl = (C == 0) ? 0 : -1;                   // column C/2-1 (unused by the first column's (1,0) tap)
+      const int dr = (j + 2 <= S.lw - 1) ? 2 : 1;         // column C/2+2, replicated at the right border
+      const float2 m0 = *reinterpret_cast<const float2*>(r0), m1 = *reinterpret_cast<const float2*>(r1);
+      const float a0 = r0[dl], d0 = r0[dr], a1 = r1[dl], d1 = r1[dr];
+      float4 v = *reinterpret_cast<const float4*>(sS + r * hc + 4 * c4);
+      const float u0 = (C == 0) ? lerp2(1.f, 0.f, wy0, wy1, m0.x, m0.y, m1.x, m1.y)
+                                : lerp2(0.25f, 0.75f, wy0, wy1, a0, m0.x, a1, m1.x);
+      const float u1 = lerp2(0.75f, 0.25f, wy0, wy1, m0.x, m0.y, m1.x, m1.y);
+      const float u2 = lerp2(0.25f, 0.75f, wy0, wy1, m0.x, m0.y, m1.x, m1.y);
+      const float u3 = lerp2(0.75f, 0.25f, wy0, wy1, m0.y, d0, m1.y, d1);
+      v.x = __fmul_rn(__fadd_rn(u0, v.x), 0.5f);
+      v.y = __fmul_rn(__fadd_rn(u1, v.y), 0.5f);
+      v.z = __fmul_rn(__fadd_rn(u2, v.z), 0.5f);
+      v.w = __fmul_rn(__fadd_rn(u3, v.w), 0.5f);
+      *reinterpret_cast<float4*>(sS + r * hc + 4 * c4) = v;
     }
-    for (int t = tid; t < NROWS; t += nthr) {     // output row -> S_s rows
-      const int y = ys + t;
-      if (y >= 0 && y < H) {
-        const Tap tp = axis_tap(S.s_hi_y, y, S.hh, H);
-        rt_i0[s * NROWS + t] = tp.i0 - hya; rt_i1[s * NROWS + t] = tp.i1 - hya;
-        rt_w0[s * NROWS + t] = tp.w0; rt_w1[s * NROWS + t] = tp.w1;
-      } else {
-        rt_i0[s * NROWS + t] = -1;
-      }
-    }
-    __syncthreads();
-    for (int c = tid; c < nhx; c += nthr) {
-      int c0, c1; float wx0, wx1;
-      tap_x2(hxa + c, S.lw, c0, c1, wx0, wx1);
-      c0 -= lxa; c1 -= lxa;
-      for (int r = 0; r < nhy; ++r) {
-        const float* r0 = sLo + p2_i0[r] * g.lc;
-        const float* r1 = sLo + p2_i1[r] * g.lc;
-        const float up = lerp2(wx0, wx1, p2_w0[r], p2_w1[r], r0[c0], r0[c1], r1[c0], r1[c1]);
-        sS[r * hc + c] = __fmul_rn(__fadd_rn(up, sS[r * hc + c]), 0.5f);
-      }
-    }
-    __syncthreads();    // sLo / p2 tables are re-used by the next scale; S_s is complete
   }
+  __syncthreads();
 
+  MSP_MARK(2);
   int hxa_s[NS];
 #pragma unroll
-  for (int s = 0; s < NS; ++s) hxa_s[s] = s_hxa[s];
+  for (int s = 0; s < NS; ++s) hxa_s[s] = s_win[s][1];
   // per-lane column taps of every scale, kept in registers: tile-relative index of the first column's
   // left tap, then per column a 2-bit offset to its own left tap (hw <= W, so 4 adjacent output columns
   // span at most 4 source columns) and 1 bit "right tap = left tap + 1"
@@ -289,8 +372,9 @@ __global__ void __launch_bounds__(32 * NW, 4) agg_nms_ms_kernel(const AggArgs a,
         for (int s = 0; s < NS; ++s) {
           const Tap tx = axis_tap(a.sc[s].s_hi_x, xe, a.sc[s].hw, W);
           const float* sS = smem + g.off_s[s];
-          const float* r0 = sS + rt_i0[s * NROWS + t] * g.hc[s];
-          const float* r1 = sS + rt_i1[s * NROWS + t] * g.hc[s];
+          const int pk = rt_pk[s * NROWS + t];
+          const float* r0 = sS + (pk & 0xff) * g.hc[s];
+          const float* r1 = sS + ((pk >> 8) & 0xff) * g.hc[s];
           const int c0 = tx.i0 - hxa_s[s], c1 = tx.i1 - hxa_s[s];
           const float vs = lerp2(tx.w0, tx.w1, rt_w0[s * NROWS + t], rt_w1[s * NROWS + t], r0[c0], r0[c1], r1[c0], r1[c1]);
           v = (s == 0) ? vs : __fadd_rn(v, vs);
@@ -301,13 +385,11 @@ __global__ void __launch_bounds__(32 * NW, 4) agg_nms_ms_kernel(const AggArgs a,
     }
   }
   __syncwarp();
+  MSP_MARK(3);
 
   // ---------------- phase 3b: walk the rows ---------------------------------------------------------------
   {
-    float hX[NS][4], hY[NS][4];   // two cached horizontally interpolated S_s rows per scale
-    int xi[NS], yi[NS];
-#pragma unroll
-    for (int s = 0; s < NS; ++s) { xi[s] = yi[s] = -1000; }
+    float hX[NS][4], hY[NS][4];   // the two horizontally interpolated S_s rows (i0, i1) of the current output row
     auto hpass = [&](int s, int r, float (&h)[4]) {
       const float* sp = smem + g.off_s[s] + r * g.hc[s];
 #pragma unroll
@@ -334,44 +416,54 @@ __global__ void __launch_bounds__(32 * NW, 4) agg_nms_ms_kernel(const AggArgs a,
       }
 #pragma unroll
       for (int s = 0; s < NS; ++s) {
-        const int i0 = rt_i0[s * NROWS + t], i1 = rt_i1[s * NROWS + t];
+        const int pk = rt_pk[s * NROWS + t];
         const float w0 = rt_w0[s * NROWS + t], w1 = rt_w1[s * NROWS + t];
-        float A[4], Bv[4];
-        if (i0 == xi[s]) {
+        const int adv = pk >> 16;                   // uniform over the CTA
+        if (adv != 0) {
+          const int i0 = pk & 0xff, i1 = (pk >> 8) & 0xff;
+          if (adv == 1) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) A[c] = hX[s][c];
-        } else if (i0 == yi[s]) {
+            for (int c = 0; c < 4; ++c) hX[s][c] = hY[s][c];
+          } else {
+            hpass(s, i0, hX[s]);
+          }
+          if (i1 == i0) {
 #pragma unroll
-          for (int c = 0; c < 4; ++c) A[c] = hY[s][c];
-        } else {
-          hpass(s, i0, A);
-        }
-        if (i1 == i0) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) Bv[c] = A[c];
-        } else if (i1 == yi[s]) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) Bv[c] = hY[s][c];
-        } else if (i1 == xi[s]) {
-#pragma unroll
-          for (int c = 0; c < 4; ++c) Bv[c] = hX[s][c];
-        } else {
-          hpass(s, i1, Bv);
+            for (int c = 0; c < 4; ++c) hY[s][c] = hX[s][c];
+          } else {
+            hpass(s, i1, hY[s]);
+          }
         }
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
-          hX[s][c] = A[c];
-          hY[s][c] = Bv[c];
-          const float vs = fmaf(w0, A[c], __fmul_rn(w1, Bv[c]));
+          const float vs = fmaf(w0, hX[s][c], __fmul_rn(w1, hY[s][c]));
           v[c] = (s == 0) ? vs : __fadd_rn(v[c], vs);
         }
-        xi[s] = i0;
-        yi[s] = i1;
       }
+      if (NS == 3) {
+        // x / 3 as two FMAs around the rounded reciprocal (checked against IEEE division for every
+        // finite float: exact for all of them but -0, which with the tiny values takes the real division)
+        const float third = 0.333333343267440796f;
+        bool odd = false;
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        if (NS > 1) v[c] = __fdiv_rn(v[c], (float)NS);
-        if (!active) v[c] = NINF;
+        for (int c = 0; c < 4; ++c) odd |= fabsf(v[c]) < 1e-30f && __float_as_uint(v[c]) != 0u;
+        if (__any_sync(kFull, odd)) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) v[c] = __fdiv_rn(v[c], 3.0f);
+        } else {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            const float q0 = __fmul_rn(v[c], third);
+            v[c] = fmaf(fmaf(-3.0f, q0, v[c]), third, q0);
+          }
+        }
+      } else if (NS > 1) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = __fdiv_rn(v[c], (float)NS);
+      }
+      if (!active) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) v[c] = NINF;
       }
     };
 
@@ -427,6 +519,12 @@ __global__ void __launch_bounds__(32 * NW, 4) agg_nms_ms_kernel(const AggArgs a,
       process_row(t, v);
     }
   }
+  MSP_MARK(4);
+#ifdef HPD_MS_PROFILE
+  if (prof)
+    printf("ms profile (cycles): tags %lld, stage+S tiles %lld, taps+halo %lld, walk %lld\n", pt[1] - pt[0], pt[2] - pt[1],
+           pt[3] - pt[2], pt[4] - pt[3]);
+#endif
 }
 
 }  // namespace ms

@@ -220,6 +220,8 @@ def _ms_scales(B, H, W, ratios, flip, seed):
     (256, 384, (0.5, 0.75), 0, False, 1),           # two scales, non-square, E = 1, NW = 2
     (512, 768, (0.5, 1.0), 0, True, 1),             # hi == output size (copy taps), several CTAs per row
     (320, 512, (0.25, 0.5), 1, True, 1),            # H not a multiple of 64
+    (128, 256, (0.25, 0.75), 1, True, 1),           # narrowest width the kernel takes (2 warps per CTA)
+    (64, 1280, (0.5, 0.75), 0, True, 1),            # two 5-warp CTAs per row band
 ])
 def test_multiscale_kernel_is_bit_identical_to_generic(H, W, ratios, tag_scale, flip, B):
     scales = _ms_scales(B, H, W, ratios, flip, seed=H + W)
