@@ -296,40 +296,66 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) agg_nms_ms_kernel(const AggA
   }
   __syncthreads();
   // ---------------- phase 2: S_s = (up2(lo_s) + hi_s) * 0.5 in place (results.py:225-226) -----------------
-  // One item = 4 adjacent half-res columns C..C+3 (C a multiple of 4) of one row: their x2 taps touch the
-  // quarter-res columns C/2-1 .. C/2+2, loaded once per row as scalar + aligned pair + scalar.
-  // (a real loop over the scales: unrolling the body only thrashes the instruction cache)
-#pragma unroll 1
-  for (int s = 0; s < NS; ++s) {
-    const ScaleDev& S = a.sc[s];
-    float* sS = smem + g.off_s[s];
-    const float* sLo = smem + g.off_lo[s];
-    const int hc = g.hc[s], lc = g.lc[s];
-    const int hya = s_win[s][0], hxa = s_win[s][1], nhy = s_win[s][2], nhx = s_win[s][3], lya = s_win[s][4], lxa = s_win[s][5];
-    const int nq = nhx >> 2, nit = nq * nhy;
-    const unsigned inv = 0xffffffffu / (unsigned)nq + 1u;     // idx / nq == umulhi(idx, inv) for idx * nq < 2^32
-    for (int idx = tid; idx < nit; idx += nthr) {
-      const int r = (int)__umulhi((unsigned)idx, inv), c4 = idx - r * nq;
-      const int C = hxa + 4 * c4, j = C >> 1, jj = j - lxa;
-      int i0, i1; float wy0, wy1;
-      tap_x2(hya + r, S.lh, i0, i1, wy0, wy1);
-      const float* r0 = sLo + (i0 - lya) * lc + jj;
-      const float* r1 = sLo + (i1 - lya) * lc + jj;
-      const int dl = (C == 0) ? 0 : -1;                   // column C/2-1 (unused by the first column's (1,0) tap)
-      const int dr = (j + 2 <= S.lw - 1) ? 2 : 1;         // column C/2+2, replicated at the right border
-      const float2 m0 = *reinterpret_cast<const float2*>(r0), m1 = *reinterpret_cast<const float2*>(r1);
-      const float a0 = r0[dl], d0 = r0[dr], a1 = r1[dl], d1 = r1[dr];
-      float4 v = *reinterpret_cast<const float4*>(sS + r * hc + 4 * c4);
-      const float u0 = (C == 0) ? lerp2(1.f, 0.f, wy0, wy1, m0.x, m0.y, m1.x, m1.y)
-                                : lerp2(0.25f, 0.75f, wy0, wy1, a0, m0.x, a1, m1.x);
-      const float u1 = lerp2(0.75f, 0.25f, wy0, wy1, m0.x, m0.y, m1.x, m1.y);
-      const float u2 = lerp2(0.25f, 0.75f, wy0, wy1, m0.x, m0.y, m1.x, m1.y);
-      const float u3 = lerp2(0.75f, 0.25f, wy0, wy1, m0.y, d0, m1.y, d1);
-      v.x = __fmul_rn(__fadd_rn(u0, v.x), 0.5f);
-      v.y = __fmul_rn(__fadd_rn(u1, v.y), 0.5f);
-      v.z = __fmul_rn(__fadd_rn(u2, v.z), 0.5f);
-      v.w = __fmul_rn(__fadd_rn(u3, v.w), 0.5f);
-      *reinterpret_cast<float4*>(sS + r * hc + 4 * c4) = v;
+  // A thread owns 4 adjacent half-res columns C..C+3 (C a multiple of 4) of one scale and walks down the
+  // rows of S_s: their x2 taps touch the quarter-res columns C/2-1 .. C/2+2 (scalar + aligned pair + scalar);
+  // a quarter-res row is interpolated horizontally once (lerp2's inner FMAs) and kept in registers for the
+  // two or three half-res rows that use it.  The column groups of all scales form one list.
+  {
+    int gstart[NS + 1];
+    gstart[0] = 0;
+#pragma unroll
+    for (int s = 0; s < NS; ++s) gstart[s + 1] = gstart[s] + (s_win[s][3] >> 2);
+    for (int gi = tid; gi < gstart[NS]; gi += nthr) {
+      int s = 0, first = 0;
+#pragma unroll
+      for (int i = 1; i < NS; ++i)
+        if (gi >= gstart[i]) { s = i; first = gstart[i]; }
+      const int c4 = gi - first;
+      const int lh = a.sc[s].lh, lw = a.sc[s].lw;
+      const int hc = g.hc[s], lc = g.lc[s];
+      const int hya = s_win[s][0], hxa = s_win[s][1], nhy = s_win[s][2], lya = s_win[s][4], lxa = s_win[s][5];
+      float* sp = smem + g.off_s[s] + 4 * c4;
+      const int C = hxa + 4 * c4, j = C >> 1;
+      const float* lp = smem + g.off_lo[s] + (j - lxa) - lya * lc;
+      const bool first_col = (C == 0);
+      const int dl = first_col ? 0 : -1;                  // column C/2-1 (unused by the first column's (1,0) tap)
+      const int dr = (j + 2 <= lw - 1) ? 2 : 1;           // column C/2+2, replicated at the right border
+      auto hp = [&](int i, float (&h)[4]) {
+        const float* rp = lp + i * lc;
+        const float2 m = *reinterpret_cast<const float2*>(rp);
+        const float l = rp[dl], r = rp[dr];
+        h[0] = first_col ? fmaf(1.f, m.x, __fmul_rn(0.f, m.y)) : fmaf(0.25f, l, __fmul_rn(0.75f, m.x));
+        h[1] = fmaf(0.75f, m.x, __fmul_rn(0.25f, m.y));
+        h[2] = fmaf(0.25f, m.x, __fmul_rn(0.75f, m.y));
+        h[3] = fmaf(0.75f, m.y, __fmul_rn(0.25f, r));
+      };
+      float hA[4] = {0.f, 0.f, 0.f, 0.f}, hB[4] = {0.f, 0.f, 0.f, 0.f};
+      int ci0 = -1, ci1 = -1;
+      for (int r = 0; r < nhy; ++r) {
+        int i0, i1; float wy0, wy1;
+        tap_x2(hya + r, lh, i0, i1, wy0, wy1);
+        if (i0 != ci0) {
+          if (i0 == ci1) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) hA[c] = hB[c];
+          } else {
+            hp(i0, hA);
+          }
+        }
+        if (i1 == i0) {
+#pragma unroll
+          for (int c = 0; c < 4; ++c) hB[c] = hA[c];
+        } else if (i1 != ci1) {
+          hp(i1, hB);
+        }
+        ci0 = i0; ci1 = i1;
+        float4 v = *reinterpret_cast<const float4*>(sp + r * hc);
+        v.x = __fmul_rn(__fadd_rn(fmaf(wy0, hA[0], __fmul_rn(wy1, hB[0])), v.x), 0.5f);
+        v.y = __fmul_rn(__fadd_rn(fmaf(wy0, hA[1], __fmul_rn(wy1, hB[1])), v.y), 0.5f);
+        v.z = __fmul_rn(__fadd_rn(fmaf(wy0, hA[2], __fmul_rn(wy1, hB[2])), v.z), 0.5f);
+        v.w = __fmul_rn(__fadd_rn(fmaf(wy0, hA[3], __fmul_rn(wy1, hB[3])), v.w), 0.5f);
+        *reinterpret_cast<float4*>(sp + r * hc) = v;
+      }
     }
   }
   __syncthreads();
