@@ -335,7 +335,7 @@ def run_ours(args):
             "grouping": {"kernel_ms": stage_ms[2], "latency_us_per_image": 1e3 * stage_ms[2],
                          "amortised_us_per_image": 1e3 * stage_ms[2] / B, "resident_warps": 4 * B,
                          "sm_occupancy_pct": 100.0 * 4 * B / (torch.cuda.get_device_properties(dev).multi_processor_count * 64),
-                         "note": "one warp per image; all images of a batch run concurrently, so the kernel duration is "
+                         "note": "one CTA of four warps per image; all images of a batch run concurrently, so the kernel duration is "
                                  "each image's latency"},
             "persons_per_image": float(n_person.mean()),
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
