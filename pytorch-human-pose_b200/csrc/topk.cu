@@ -23,7 +23,6 @@ namespace hpd {
 namespace {
 
 constexpr int kTopkWarps = 4;
-constexpr int kLogCap = 768;   // entering elements logged per row (typical: 100-300)
 
 struct HeapRef {
   float* v;
@@ -107,6 +106,98 @@ struct HeapSink {
     __syncwarp();
     top = h.v[0];
   }
+  template <bool EQ>
+  __device__ __forceinline__ void feed(float cv, int idx) {
+    if (cv > top) insert(cv, idx);
+  }
+};
+
+// ---- exact sink, warp-wide: the same libstdc++ heap with slot i held by lane i --------------------------
+// __adjust_heap walks down choosing, per level, between two siblings, then __push_heap walks back up
+// comparing the value with the elements of that path.  Both kinds of comparison are made for the whole
+// heap at once -- lane k compares node k's two children, every lane compares its element with the value
+// -- and collected by two ballots; the walk itself is then scalar bit arithmetic, and all element moves
+// along the path are one shuffle.  Same comparisons, same outcome as the functions above, ~3x fewer
+// cycles per insertion than lane 0 editing shared memory.
+struct WarpHeap {
+  int lane;
+  float v;
+  int i;
+  __device__ __forceinline__ void adjust(int hole, int len, float val, int idx) {
+    const int lc = min(2 * lane + 1, 31), rc = min(2 * lane + 2, 31);
+    const float right = __shfl_sync(kFull, v, rc), left = __shfl_sync(kFull, v, lc);
+    const unsigned take_left = __ballot_sync(kFull, comp_gt(right, left));   // bit k: comp(first[2k+2], first[2k+1])
+    const unsigned above = __ballot_sync(kFull, comp_gt(v, val));            // bit n: comp(first[n], value)
+    int p[7];
+    p[0] = hole;
+    int n = 0, child = hole;
+    bool finished = false;
+#pragma unroll
+    for (int k = 1; k <= 6; ++k) {
+      p[k] = 0;
+      if (!finished) {
+        if (child < (len - 1) / 2) {
+          int c = 2 * (child + 1);
+          if ((take_left >> child) & 1u) --c;
+          p[k] = c; n = k; child = c;
+        } else {
+          if ((len & 1) == 0 && child == (len - 2) / 2) { p[k] = 2 * (child + 1) - 1; n = k; }
+          finished = true;
+        }
+      }
+    }
+    // __push_heap from the leaf: climbs while the element above (the one just moved up) is greater
+    int j = n;
+#pragma unroll
+    for (int k = 6; k >= 1; --k)
+      if (k <= n && j == k && ((above >> p[k]) & 1u)) j = k - 1;
+    int src = lane;
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+      if (k < j && lane == p[k]) src = p[k + 1];
+    const float nv = __shfl_sync(kFull, v, src);
+    const int ni = __shfl_sync(kFull, i, src);
+    v = nv; i = ni;
+    int pj = p[0];
+#pragma unroll
+    for (int k = 1; k <= 6; ++k)
+      if (k == j) pj = p[k];
+    if (lane == pj) { v = val; i = idx; }
+  }
+  __device__ __forceinline__ void make(int len) {
+    if (len < 2) return;
+    for (int parent = (len - 2) / 2; parent >= 0; --parent)
+      adjust(parent, len, __shfl_sync(kFull, v, parent), __shfl_sync(kFull, i, parent));
+  }
+  __device__ __forceinline__ void sort(int len) {
+    for (int last = len - 1; last >= 1; --last) {
+      const float val = __shfl_sync(kFull, v, last), v0 = __shfl_sync(kFull, v, 0);
+      const int idx = __shfl_sync(kFull, i, last), i0 = __shfl_sync(kFull, i, 0);
+      if (lane == last) { v = v0; i = i0; }
+      adjust(0, last, val, idx);
+    }
+  }
+};
+
+struct WarpHeapSink {
+  WarpHeap h;
+  int M, lane;
+  float top;
+  __device__ __forceinline__ void init(float nv) {   // lane < M holds element `lane` of the row
+    h.lane = lane;
+    h.v = nv;
+    h.i = lane;
+    h.make(M);
+    top = __shfl_sync(kFull, h.v, 0);
+  }
+  __device__ __forceinline__ void insert(float cv, int idx) {
+    h.adjust(0, M, cv, idx);
+    top = __shfl_sync(kFull, h.v, 0);
+  }
+  template <bool EQ>
+  __device__ __forceinline__ void feed(float cv, int idx) {
+    if (cv > top) insert(cv, idx);
+  }
 };
 
 // ---- fast sink: the M kept elements sorted by value across the lanes of the warp ---------------------
@@ -140,9 +231,25 @@ struct SortedSink {
     rej_eq = -INFINITY;
     any_evicted = false;
   }
-  __device__ __forceinline__ void offer(float cv, int idx) {   // merge step: any value may be offered
+  // M placeholders of value `floor_v` (index -1): for a row known to hold at least M elements above
+  // floor_v the placeholders are all evicted by the end, and nothing at or below floor_v is ever looked at
+  __device__ __forceinline__ void init_floor(float floor_v) {
+    n_log = 0;
+    sv = lane < M ? floor_v : -INFINITY;
+    si = -1;
+    top = floor_v;
+    evicted = -INFINITY;
+    rej_eq = -INFINITY;
+    any_evicted = false;
+  }
+  __device__ __forceinline__ void offer(float cv, int idx) {   // any value may be offered
     if (cv > top) insert(cv, idx);
     else if (cv == top) rej_eq = cv;
+  }
+  template <bool EQ>
+  __device__ __forceinline__ void feed(float cv, int idx) {
+    if (EQ) offer(cv, idx);
+    else if (cv > top) insert(cv, idx);
   }
   __device__ __forceinline__ void init(float nv) {
     n_log = 0;
@@ -191,7 +298,9 @@ struct SortedSink {
 // (the next 128 are prefetched while this group is processed); words that can still hold an
 // entering element are expanded up to 8 at a time so that their heatmap lines and mask words are
 // fetched together instead of one DRAM round trip each.
-template <typename Sink>
+// EQ: elements EQUAL to the sink's smallest kept value are fed too (the floor mode needs to see them to
+// know whether its result is free of ties); otherwise only strictly greater ones, as the heap admits.
+template <typename Sink, bool EQ = false>
 __device__ __forceinline__ void scan_range(Sink& sink, const float* __restrict__ hm, const uint32_t* __restrict__ mk,
                                            const float* __restrict__ wm, int W, int wpr, int w_begin, int w_end,
                                            int first_idx, int lane) {
@@ -221,7 +330,7 @@ __device__ __forceinline__ void scan_range(Sink& sink, const float* __restrict__
 #pragma unroll
     for (int u = 0; u < kGroup; ++u) {
       const int cbase = base + 32 * u;
-      uint32_t pass = __ballot_sync(kFull, cur[u] > sink.top);
+      uint32_t pass = __ballot_sync(kFull, EQ ? (cur[u] >= sink.top) : (cur[u] > sink.top));
       while (pass) {
         float hv[kSlots];
         uint32_t mw[kSlots];
@@ -245,24 +354,66 @@ __device__ __forceinline__ void scan_range(Sink& sink, const float* __restrict__
 #pragma unroll
         for (int s = 0; s < kSlots; ++s) {
           if (wl[s] < 0) break;
-          if (!(__shfl_sync(kFull, cur[u], wl[s]) > sink.top)) continue;   // the top may have risen meanwhile
+          const float wmx = __shfl_sync(kFull, cur[u], wl[s]);
+          if (!(EQ ? (wmx >= sink.top) : (wmx > sink.top))) continue;   // the top may have risen meanwhile
           const int w2 = cbase + wl[s];
           const int y = w2 / wpr, x0 = (w2 - y * wpr) * 32;
           const bool valid = (x0 + lane < W) && (y * W + x0 + lane >= first_idx);
           const bool keep = (mw[s] >> lane) & 1u;
           const float nv = keep ? hv[s] : __fmul_rn(hv[s], 0.0f);
-          uint32_t cand = __ballot_sync(kFull, valid && nv > sink.top);
+          uint32_t cand = __ballot_sync(kFull, valid && (EQ ? (nv >= sink.top) : (nv > sink.top)));
           while (cand) {
             const int j = __ffs(cand) - 1;
             cand &= cand - 1;
             const float cv = __shfl_sync(kFull, nv, j);
-            if (cv > sink.top) sink.insert(cv, y * W + x0 + j);
+            sink.template feed<EQ>(cv, y * W + x0 + j);
           }
         }
       }
     }
   }
 }
+
+// ---- a floor for the M-th largest value of words [w_begin, w_end) -------------------------------------
+// Every word maximum is the NMS'd value of a distinct pixel, so the M-th largest of any set of word
+// maxima is a lower bound of the M-th largest pixel value.  Each lane keeps the 4 largest of the maxima it
+// streams (the true top M are spread over the lanes, so the 128 candidates nearly always contain them);
+// pop() removes the largest candidate of the warp.
+struct WordMaxCandidates {
+  float t0, t1, t2, t3;   // descending
+  __device__ __forceinline__ void scan(const float* __restrict__ wm, int w_begin, int w_end, int lane) {
+    t0 = t1 = t2 = t3 = -INFINITY;
+    constexpr int U = 8;
+    for (int base = w_begin; base < w_end; base += 32 * U) {
+      float v[U];
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const int wd = base + 32 * u + lane;
+        v[u] = wd < w_end ? wm[wd] : -INFINITY;
+      }
+#pragma unroll
+      for (int u = 0; u < U; ++u) {
+        const float a = fminf(t0, v[u]); t0 = fmaxf(t0, v[u]);
+        const float b = fminf(t1, a);    t1 = fmaxf(t1, a);
+        const float c = fminf(t2, b);    t2 = fmaxf(t2, b);
+        t3 = fmaxf(t3, c);
+      }
+    }
+  }
+  __device__ __forceinline__ float pop(int lane) {
+    // order-preserving float -> unsigned map, warp max, the lowest lane holding it drops its head
+    const unsigned bits = __float_as_uint(t0);
+    const unsigned key = bits ^ ((bits >> 31) ? 0xffffffffu : 0x80000000u);
+    const unsigned mx = __reduce_max_sync(kFull, key);
+    const unsigned owners = __ballot_sync(kFull, key == mx);
+    if (lane == __ffs(owners) - 1) { t0 = t1; t1 = t2; t2 = t3; t3 = -INFINITY; }
+    const unsigned ob = mx ^ ((mx >> 31) ? 0x80000000u : 0xffffffffu);
+    return __uint_as_float(ob);
+  }
+};
+
+// largest float below a positive finite x
+__device__ __forceinline__ float next_below(float x) { return __uint_as_float(__float_as_uint(x) - 1u); }
 
 // NMS'd value of flat element `lane` (the sequential algorithm's initial heap is elements 0..M-1)
 __device__ __forceinline__ float first_element(const float* __restrict__ hm, const uint32_t* __restrict__ mk, int W,
@@ -295,8 +446,6 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __re
                                                               float* __restrict__ tags_k) {
   __shared__ float s_v[kTopkWarps][32];
   __shared__ int s_i[kTopkWarps][32];
-  __shared__ float s_logv[kTopkWarps][kLogCap];
-  __shared__ int s_logi[kTopkWarps][kLogCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kTopkWarps + warp;
   if (row >= rows) return;
@@ -307,28 +456,40 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __re
   float out_v = 0.f;
   int out_i = 0;
   bool done = false;
-  int n_logged = -1;   // >= 0: the fast pass logged every entering element of this row
   if (!force_exact) {
-    SortedSink fast;
-    fast.M = M; fast.lane = lane;
-    fast.log_v = s_logv[warp]; fast.log_i = s_logi[warp]; fast.log_cap = kLogCap;
-    scan_row(fast, hm, mk, wm, H, W, wpr, M, lane);
-    if (!fast.ambiguous()) { out_v = fast.sv; out_i = fast.si; done = true; }
-    else n_logged = fast.n_log;
+    // Floor mode: with M word maxima above a positive floor the row holds M positive peaks, the stream can
+    // start at that floor instead of at the row's first M elements, and only a few dozen words are ever
+    // expanded.  Its value history is not the heap's, so it is only final when the result is free of ties
+    // (distinct kept values, nothing else in the row equal to the smallest) -- then the M largest values in
+    // descending order are what any history produces.
+    WordMaxCandidates cand;
+    cand.scan(wm, 0, H * wpr, lane);
+    float floor_v = 0.f;
+    for (int i = 0; i < M; ++i) floor_v = cand.pop(lane);
+    if (floor_v > 0.f) {
+      SortedSink fl;
+      fl.M = M; fl.lane = lane;
+      fl.log_v = nullptr; fl.log_i = nullptr; fl.log_cap = 0;
+      fl.init_floor(next_below(floor_v));
+      scan_range<SortedSink, true>(fl, hm, mk, wm, W, wpr, 0, H * wpr, 0, lane);
+      if (!fl.ambiguous()) { out_v = fl.sv; out_i = fl.si; done = true; }
+    }
   }
-  if (!done) {   // ties in play: replay the row with the exact libstdc++ heap
+  if (!done && !force_exact) {
+    // ties in play (always so for a channel with fewer than M positive peaks: its +-0 tail): stream the
+    // row through the exact heap, slot i in lane i
+    WarpHeapSink exact;
+    exact.M = M; exact.lane = lane;
+    scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
+    exact.h.sort(M);
+    out_v = exact.h.v; out_i = exact.h.i;
+    done = true;
+  }
+  if (!done) {   // force_exact: the literal libstdc++ control flow, lane 0 editing shared memory
     HeapSink exact;
     exact.h = HeapRef{s_v[warp], s_i[warp]};
     exact.M = M; exact.lane = lane;
-    if (n_logged >= 0 && n_logged <= kLogCap) {
-      // same entering elements, same order: build the heap from the first M elements and feed the log
-      exact.init(first_element(hm, mk, W, wpr, M, lane));
-      __syncwarp();
-      if (lane == 0)
-        for (int i = 0; i < n_logged; ++i) adjust_heap(exact.h, 0, M, s_logv[warp][i], s_logi[warp][i]);
-    } else {
-      scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
-    }
+    scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
     __syncwarp();
     if (lane == 0) sort_heap(exact.h, M);
     __syncwarp();
@@ -368,17 +529,81 @@ __global__ void __launch_bounds__(kSplitWarps * 32) topk_split_kernel(const floa
   __shared__ float s_logv[kSplitWarps][kSegLogCap];
   __shared__ int s_logi[kSplitWarps][kSegLogCap];
   __shared__ float s_evicted[kSplitWarps];
+  __shared__ float s_rej[kSplitWarps];
   __shared__ int s_nlog[kSplitWarps];
+  __shared__ float s_cand[kSplitWarps][8];
+  __shared__ int s_floor_done;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x;
   const float* hm = agg_hm + (size_t)row * H * W;
   const uint32_t* mk = mask + (size_t)row * H * wpr;
   const float* wm = wmax + (size_t)row * H * wpr;
   const int nwords = H * wpr;
+  const int groups = (nwords + 127) / 128;   // segment bounds in whole groups of 128 words
+  const int gb = (groups * warp) / kSplitWarps, ge = (groups * (warp + 1)) / kSplitWarps;
 
   if (!force_exact) {
-    const int groups = (nwords + 127) / 128;   // segment bounds in whole groups of 128 words
-    const int gb = (groups * warp) / kSplitWarps, ge = (groups * (warp + 1)) / kSplitWarps;
+    // Floor mode (see topk_kernel): the floor is the M-th largest of the 8 largest word maxima of every
+    // segment; each segment then keeps its elements above it and warp 0 merges.  Final only when free of
+    // ties: distinct values, and no segment saw, evicted or turned away another element equal to the M-th.
+    WordMaxCandidates cand;
+    cand.scan(wm, gb * 128, min(ge * 128, nwords), lane);
+    for (int r = 0; r < 8; ++r) {
+      const float x = cand.pop(lane);
+      if (lane == 0) s_cand[warp][r] = x;
+    }
+    if (threadIdx.x == 0) s_floor_done = 0;
+    __syncthreads();
+    static_assert(kSplitWarps * 8 == 64, "two candidates per lane below");
+    const float c0 = (&s_cand[0][0])[2 * lane], c1 = (&s_cand[0][0])[2 * lane + 1];
+    cand.t0 = fmaxf(c0, c1); cand.t1 = fminf(c0, c1); cand.t2 = cand.t3 = -INFINITY;
+    float floor_v = 0.f;
+    for (int r = 0; r < M; ++r) floor_v = cand.pop(lane);
+    if (floor_v > 0.f) {   // uniform over the CTA
+      SortedSink seg;
+      seg.M = M; seg.lane = lane;
+      seg.log_v = nullptr; seg.log_i = nullptr; seg.log_cap = 0;
+      seg.init_floor(next_below(floor_v));
+      scan_range<SortedSink, true>(seg, hm, mk, wm, W, wpr, gb * 128, min(ge * 128, nwords), 0, lane);
+      s_v[warp][lane] = seg.sv;
+      s_i[warp][lane] = seg.si;
+      if (lane == 0) {
+        s_evicted[warp] = seg.any_evicted ? seg.evicted : -INFINITY;
+        s_rej[warp] = seg.rej_eq;
+      }
+      __syncthreads();
+      if (warp == 0) {
+        SortedSink all;
+        all.M = M; all.lane = lane;
+        all.log_v = nullptr; all.log_i = nullptr; all.log_cap = 0;
+        all.init_empty();
+        for (int w = 0; w < kSplitWarps; ++w) {
+          const float cvl = s_v[w][lane];
+          const int cil = s_i[w][lane];
+          for (int j = 0; j < M; ++j) {           // descending; placeholders (index -1) come last
+            const float cv = __shfl_sync(kFull, cvl, j);
+            const int ci = __shfl_sync(kFull, cil, j);
+            if (ci < 0 || cv < all.top) break;
+            all.offer(cv, ci);
+          }
+        }
+        bool amb = all.ambiguous();
+        for (int w = 0; w < kSplitWarps; ++w) amb = amb || (s_evicted[w] == all.top) || (s_rej[w] == all.top);
+        if (!amb) {
+          if (lane < M) {
+            const size_t o = (size_t)row * M + lane;
+            scores_k[o] = all.sv;
+            idx_k[o] = all.si;
+            coords_k[o * 2 + 0] = all.si % W;
+            coords_k[o * 2 + 1] = all.si / W;
+            for (int e = 0; e < E; ++e) tags_k[o * E + e] = agg_tags[((size_t)row * H * W + all.si) * E + e];
+          }
+          if (lane == 0) s_floor_done = 1;
+        }
+      }
+      __syncthreads();
+      if (s_floor_done) return;
+    }
     SortedSink seg;
     seg.M = M; seg.lane = lane;
     seg.log_v = s_logv[warp]; seg.log_i = s_logi[warp]; seg.log_cap = kSegLogCap;
@@ -416,39 +641,37 @@ __global__ void __launch_bounds__(kSplitWarps * 32) topk_split_kernel(const floa
     for (int w = 0; w < kSplitWarps; ++w) amb = amb || (s_evicted[w] == all.top);
     if (!amb) { out_v = all.sv; out_i = all.si; done = true; }
   }
-  if (!done) {
+  if (!done && logs_ok) {
+    // the logs hold a superset of the entering elements in index order: filter 32 entries at a time
+    // against the live top, replay the survivors one by one through the exact heap (slot i in lane i)
+    WarpHeapSink exact;
+    exact.M = M; exact.lane = lane;
+    exact.init(first_element(hm, mk, W, wpr, M, lane));
+    for (int w = 0; w < kSplitWarps; ++w) {
+      const int n = s_nlog[w];
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const float cv = i < n ? s_logv[w][i] : -INFINITY;
+        const int ci = i < n ? s_logi[w][i] : 0;
+        uint32_t pass = __ballot_sync(kFull, i < n && ci >= M && cv > exact.top);
+        while (pass) {
+          const int j = __ffs(pass) - 1;
+          pass &= pass - 1;
+          const float cvj = __shfl_sync(kFull, cv, j);
+          const int cij = __shfl_sync(kFull, ci, j);
+          if (cvj > exact.top) exact.insert(cvj, cij);
+        }
+      }
+    }
+    exact.h.sort(M);
+    out_v = exact.h.v; out_i = exact.h.i;
+    done = true;
+  }
+  if (!done) {   // force_exact, or a log overflowed: the literal libstdc++ control flow over the whole row
     HeapSink exact;
     exact.h = HeapRef{s_v[0], s_i[0]};
     exact.M = M; exact.lane = lane;
-    if (logs_ok) {
-      exact.init(first_element(hm, mk, W, wpr, M, lane));
-      __syncwarp();
-      // the logs hold a superset of the entering elements in index order: filter 32 entries at a time
-      // against the live top, replay the survivors one by one
-      float top = exact.top;
-      for (int w = 0; w < kSplitWarps; ++w) {
-        const int n = s_nlog[w];
-        for (int i0 = 0; i0 < n; i0 += 32) {
-          const int i = i0 + lane;
-          const float cv = i < n ? s_logv[w][i] : -INFINITY;
-          const int ci = i < n ? s_logi[w][i] : 0;
-          uint32_t pass = __ballot_sync(kFull, i < n && ci >= M && cv > top);
-          while (pass) {
-            const int j = __ffs(pass) - 1;
-            pass &= pass - 1;
-            const float cvj = __shfl_sync(kFull, cv, j);
-            const int cij = __shfl_sync(kFull, ci, j);
-            if (cvj > top) {
-              if (lane == 0) adjust_heap(exact.h, 0, M, cvj, cij);
-              __syncwarp();
-              top = exact.h.v[0];
-            }
-          }
-        }
-      }
-    } else {
-      scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
-    }
+    scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
     __syncwarp();
     if (lane == 0) sort_heap(exact.h, M);
     __syncwarp();
