@@ -171,6 +171,38 @@ def test_decode_matches_committed_reference_goldens(name):
     assert np.array_equal(gj, g["grouped_joints"]) and np.array_equal(ps, g["person_scores"])
 
 
+@pytest.mark.parametrize("size,levels,peaks", [
+    (256, 64, 400),      # plenty of positive peaks on a coarse value grid: ties inside the top 30 and at its boundary
+    (256, 4096, 60),     # few ties: the floor-mode result stands for most joints
+    (128, 16, 25),       # fewer than 30 positive peaks: +-0 tail, one warp per row (too small for the split kernel)
+    (512, 32, 2000),     # 8 warps per row with heavy ties
+])
+def test_topk_tie_order_matches_oracle(size, levels, peaks, oracle):
+    """Top-k on heatmaps built to tie: isolated peaks with values on a coarse grid over a negative background.
+    Indices, values and tags must be the reference's (std::partial_sort history order among equal values)."""
+    from hpdecode import MPPEHeatmapParser
+    rng = np.random.default_rng(size + levels + peaks)
+    K = 17
+    hm = -rng.random((K, size, size), dtype=np.float32) - 0.5
+    for k in range(K):
+        n = peaks if k % 3 else max(peaks // 8, 3)                 # every third joint has few peaks
+        ys = rng.integers(2, size - 2, n)
+        xs = rng.integers(2, size - 2, n)
+        hm[k, ys, xs] = (rng.integers(1, levels + 1, n) / np.float32(levels)).astype(np.float32)
+    tg = rng.standard_normal((K, size, size, 2)).astype(np.float32)
+    parser = MPPEHeatmapParser(K, 30, 0.05, 0.5)
+    tags_k, coords_k, scores_k = parser.top_k(torch.from_numpy(hm), torch.from_numpy(tg))
+    nm, _ = oracle.nms(hm)
+    want = oracle.top_k(nm, tg, 30)
+    w_tags, w_coords, w_scores = want[0], want[1], want[2]
+    assert np.array_equal(coords_k, w_coords)
+    assert np.array_equal(_bits(scores_k), _bits(w_scores)) and np.array_equal(_bits(tags_k), _bits(w_tags))
+    # and the reference's own call (grouping.py:153): torch's CPU topk on the flattened NMS'd map
+    tv, ti = torch.from_numpy(nm).reshape(K, -1).topk(30, dim=1)
+    assert np.array_equal(coords_k[..., 1] * size + coords_k[..., 0], ti.numpy())
+    assert np.array_equal(_bits(scores_k), _bits(tv.numpy()))
+
+
 @pytest.mark.parametrize("gen,kw,size", [
     ("netlike", dict(batch=2, size=256, flip=True, seed=61), 256),
     ("crowd", dict(batch=2, size=256, persons=25, flip=True, seed=62, quantised=True), 256),
