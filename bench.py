@@ -138,10 +138,16 @@ def workload_config(args):
 # GPU side
 # ------------------------------------------------------------------------------------------------
 class ClockSampler:
-    Q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+    """nvidia-smi polling SM clock and throttle reasons every 20 ms.  It needs a few hundred ms to attach, so it
+    is started early; only the samples stamped inside [mark_start(), stop()] -- the timed regions -- are kept."""
+    Q = "timestamp,clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
+    def mark_start(self):
+        self.t0 = time.time()
+
     def __init__(self, index: int):
+        self.t0 = time.time()
         self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
         try:
             self.p = subprocess.Popen(["nvidia-smi", "-i", str(index), f"--query-gpu={self.Q}",
@@ -149,11 +155,18 @@ class ClockSampler:
                                       stderr=subprocess.DEVNULL)
         except Exception:
             self.p = None
+        import atexit
+        atexit.register(self._kill)       # never leave the poller behind if the run dies before stop()
+
+    def _kill(self):
+        if self.p is not None and self.p.poll() is None:
+            self.p.kill()
 
     def stop(self):
         out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
         if self.p is None:
             return out
+        t1 = time.time()
         self.p.terminate()
         try:
             self.p.wait(timeout=5)
@@ -161,18 +174,22 @@ class ClockSampler:
             self.p.kill()
         self.f.flush()
         self.f.seek(0)
+        import datetime
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ln in self.f.read().splitlines():
             parts = [x.strip() for x in ln.split(",")]
-            if len(parts) < 6:
+            if len(parts) < 7:
                 continue
             try:
-                sm.append(float(parts[0]))
-                mx.append(float(parts[1]))
+                ts = datetime.datetime.strptime(parts[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                if not (self.t0 - 0.02 <= ts <= t1 + 0.02):
+                    continue
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
             except ValueError:
                 continue
-            for n, v in zip(names, parts[2:6]):
+            for n, v in zip(names, parts[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         os.unlink(self.f.name)
@@ -207,6 +224,7 @@ def run_ours(args):
     dev = torch.device("cuda", local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+    sampler = ClockSampler(local) if rank == 0 else None     # attaches while the inputs are produced
 
     B, S = args.batch, args.size
     if args.inputs == "hrnet":
@@ -265,8 +283,8 @@ def run_ours(args):
 
     # ---- value: inputs resident in HBM -------------------------------------------------------------
     run_steps(max(args.warmup, 3) * NS, value_step)
-    sampler = ClockSampler(local) if rank == 0 else None
-    time.sleep(0.2 if rank == 0 else 0.0)     # let nvidia-smi attach before the timed work starts
+    if sampler:
+        sampler.mark_start()
     # per-stage durations: K sequential steps, one batch in flight, CUDA events on the launching stream
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(args.steps)]
     for i in range(args.steps):
