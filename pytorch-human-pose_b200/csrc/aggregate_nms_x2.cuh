@@ -167,6 +167,177 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float*
   }
 }
 
+// The NMS half of the column walk, shared by the x2 and the multi-scale kernel.  A lane owns 4 adjacent
+// output columns and is fed their values row by row (t = index of the row in the walk, row y = ys + t, rows
+// outside the image carry -inf).  Every row is stored to the aggregated heatmap (if it belongs to the band),
+// reduced to its 5-wide row maximum (own 4 + 2 from each neighbour lane, the strip's halo columns from
+// `edge`), and pushed into a register window: r0..r3 = row maxima of rows y-4..y-1, vq0 / vq1 = values of
+// rows y-2 / y-1.  The centre row y-2 then gets its 5-tall column maximum, survivor bits (grouping.py:80-83)
+// and the per-word side arrays (survivor mask, maximum of the survivors, maximum of the raw values).
+template <int RB>
+struct NmsColumnWalk {
+  float r0[4], r1[4], r2[4], r3[4], vq0[4], vq1[4];
+  float* hm_plane;
+  const float* edge;
+  size_t wbase;
+  int ys, lane, shl;
+  bool active, word_writer;
+
+  __device__ __forceinline__ void init(const AggArgs& a, int b, int k, int X0, int ys_, const float* edge_, bool active_,
+                                       int lane_) {
+#pragma unroll
+    for (int c = 0; c < 4; ++c) { r0[c] = r1[c] = r2[c] = r3[c] = -INFINITY; vq0[c] = vq1[c] = -INFINITY; }
+    hm_plane = a.agg_hm + ((size_t)b * a.K + k) * a.H * a.W + X0;
+    wbase = ((size_t)b * a.K + k) * a.H * a.wpr + (X0 >> 5);
+    edge = edge_;
+    ys = ys_; lane = lane_; active = active_;
+    word_writer = active_ && (lane_ & 7) == 0;
+    shl = 4 * (lane_ & 7);
+  }
+
+  __device__ __forceinline__ void row(const AggArgs& a, int t, const float (&v)[4]) {
+    const int H = a.H, W = a.W;
+    const int y = ys + t;
+    if (t >= 2 && t < RB + 2 && y < H && active)
+      *reinterpret_cast<float4*>(hm_plane + (size_t)y * W) = make_float4(v[0], v[1], v[2], v[3]);
+    float l2 = __shfl_up_sync(kFull, v[2], 1), l3 = __shfl_up_sync(kFull, v[3], 1);
+    float q0 = __shfl_down_sync(kFull, v[0], 1), q1 = __shfl_down_sync(kFull, v[1], 1);
+    if (lane == 0) { const float2 e = *reinterpret_cast<const float2*>(edge + t * 4); l2 = e.x; l3 = e.y; }
+    if (lane == 31) { const float2 e = *reinterpret_cast<const float2*>(edge + t * 4 + 2); q0 = e.x; q1 = e.y; }
+    const float pb = fmaxf(v[0], v[1]), pc = fmaxf(v[2], v[3]);
+    float rm[4];
+    rm[0] = max3(fmaxf(l2, l3), pb, v[2]);
+    rm[1] = max3(l3, pb, pc);
+    rm[2] = max3(pb, pc, q0);
+    rm[3] = max3(v[1], pc, fmaxf(q0, q1));
+    const int yc = y - 2;
+    if (t >= 4 && yc < H) {   // uniform over the CTA
+      const float m0 = max3(max3(r0[0], r1[0], r2[0]), r3[0], rm[0]);
+      const float m1 = max3(max3(r0[1], r1[1], r2[1]), r3[1], rm[1]);
+      const float m2 = max3(max3(r0[2], r1[2], r2[2]), r3[2], rm[2]);
+      const float m3 = max3(max3(r0[3], r1[3], r2[3]), r3[3], rm[3]);
+      const bool k0 = (m0 == vq0[0]), k1 = (m1 == vq0[1]), k2 = (m2 == vq0[2]), k3 = (m3 == vq0[3]);
+      // NMS'd value of a suppressed pixel is +-0; its sign cannot change any comparison made on the word maximum
+      float wm4 = fmaxf(fmaxf(k0 ? vq0[0] : 0.f, k1 ? vq0[1] : 0.f), fmaxf(k2 ? vq0[2] : 0.f, k3 ? vq0[3] : 0.f));
+      float hm4 = fmaxf(fmaxf(vq0[0], vq0[1]), fmaxf(vq0[2], vq0[3]));
+      unsigned bits = ((k0 ? 1u : 0u) | (k1 ? 2u : 0u) | (k2 ? 4u : 0u) | (k3 ? 8u : 0u)) << shl;
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        bits |= __shfl_xor_sync(kFull, bits, o);
+        hm4 = fmaxf(hm4, __shfl_xor_sync(kFull, hm4, o));
+        wm4 = fmaxf(wm4, __shfl_xor_sync(kFull, wm4, o));
+      }
+      if (word_writer) {
+        const size_t w = wbase + (size_t)yc * a.wpr;
+        a.mask[w] = bits;
+        a.wmax[w] = wm4;
+        a.hmax[w] = hm4;
+      }
+    }
+#pragma unroll
+    for (int c = 0; c < 4; ++c) {
+      r0[c] = r1[c]; r1[c] = r2[c]; r2[c] = r3[c]; r3[c] = rm[c];
+      vq0[c] = vq1[c]; vq1[c] = v[c];
+    }
+  }
+};
+
+// Tags of one band: x4 bilinear taps (results.py:229-230) from the staged quarter-res tag tiles sT
+// ([E][TR][tc], tile origin column txo, tile row r = quarter-res row y0/4 - 1 + r) to the E-innermost
+// output, for the lane's 4 output columns X0..X0+3 and the RB rows from y0; plus the per (4 rows x 32
+// columns) range of the first tag component (tag_bmin / tag_bmax, the refine prefilter).  Called by the
+// lanes whose columns are inside the image (W % 32 == 0: whole 8-lane word groups).
+template <int E, int RB, int TR>
+__device__ __forceinline__ void tags_x4_band(const AggArgs& a, const float* __restrict__ sT, int tc, int txo, int X0,
+                                             int y0, int b, int k, int lane) {
+  const int H = a.H, W = a.W;
+  const int q = X0 >> 2;                       // this lane's quarter-res column
+  const int tb = q - 1 - txo;                  // index of T[q-1] in a tile row
+  const bool x_first = (q == 0);
+  // columns 4q+{0,1}: taps (q-1,q) weights (.375,.625),(.125,.875); 4q+{2,3}: (q,q+1) (.875,.125),(.625,.375)
+  const float wa0 = x_first ? 1.f : 0.375f, wb0 = x_first ? 0.f : 0.625f;
+  const float wa1 = x_first ? 1.f : 0.125f, wb1 = x_first ? 0.f : 0.875f;
+  float hA[E][4], hB[E][4];
+  // also returns the range of the sources of the FIRST tag component: every output it contributes to
+  // is a convex combination of them (refine prefilter, tag_bmin / tag_bmax)
+  auto hpass = [&](int r, float (&h)[E][4], float& mn, float& mx) {
+#pragma unroll
+    for (int e = 0; e < E; ++e) {
+      const float* t = sT + e * TR * tc + r * tc + tb;
+      const float t0 = t[0], t1 = t[1], t2 = t[2];
+      if (e == 0) { mn = fminf(fminf(t0, t1), t2); mx = fmaxf(fmaxf(t0, t1), t2); }
+      const float a0 = x_first ? t1 : t0, b0 = x_first ? t2 : t1;
+      h[e][0] = fmaf(wa0, a0, __fmul_rn(wb0, b0));
+      h[e][1] = fmaf(wa1, a0, __fmul_rn(wb1, b0));
+      h[e][2] = fmaf(0.875f, t1, __fmul_rn(0.125f, t2));
+      h[e][3] = fmaf(0.625f, t1, __fmul_rn(0.375f, t2));
+    }
+  };
+  float* tg_plane = a.agg_tags + ((size_t)b * a.K + k) * H * W * E;
+  auto emit = [&](int y, float wy0, float wy1, const float (&A)[E][4], const float (&Bv)[E][4]) {
+    if (y < y0 || y >= y0 + RB || y >= H) return;
+    float o[E][4];
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) o[e][c] = fmaf(wy0, A[e][c], __fmul_rn(wy1, Bv[e][c]));
+    float* dst = tg_plane + ((size_t)y * W + X0) * E;
+    if (E == 1) {
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
+    } else {
+      *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[E - 1][0], o[0][1], o[E - 1][1]);
+      *reinterpret_cast<float4*>(dst + 4) = make_float4(o[0][2], o[E - 1][2], o[0][3], o[E - 1][3]);
+    }
+  };
+  // tile rows: r <-> quarter-res row tyo + r = y0/4 - 1 + r.  Rows y0, y0+1 use (i-1, i) with
+  // i = y0/4, i.e. tile rows (0, 1); then each group of 4 rows 4i+2..4i+5 uses rows (i, i+1).
+  const unsigned amask = __activemask();      // W % 32 == 0: whole 8-lane word groups are active
+  float mnA, mxA, mnB, mxB, mnC, mxC;
+  hpass(0, hA, mnA, mxA);
+  hpass(1, hB, mnB, mxB);
+  if (y0 == 0) {          // first two rows of the image: src clamps to 0 -> taps (row 0, row 1), weights (1, 0)
+    float hC[E][4];
+    hpass(2, hC, mnC, mxC);   // tile row 1 = image row 0, tile row 2 = image row 1
+    emit(0, 1.f, 0.f, hB, hC);
+    emit(1, 1.f, 0.f, hB, hC);
+  } else {
+    emit(y0, 0.375f, 0.625f, hA, hB);
+    emit(y0 + 1, 0.125f, 0.875f, hA, hB);
+  }
+  const int HB = (H + 3) >> 2;
+  const size_t bbase = (((size_t)b * a.K + k) * HB + (y0 >> 2)) * a.wpr + (X0 >> 5);
+#pragma unroll 1
+  for (int g = 0; g < RB / 4; ++g) {
+    // rows y0 + 4g + 2 .. y0 + 4g + 5 : taps (tile row g+1, tile row g+2)
+#pragma unroll
+    for (int e = 0; e < E; ++e)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) hA[e][c] = hB[e][c];
+    hpass(g + 2, hB, mnC, mxC);
+    // band of rows y0+4g .. y0+4g+3 reads tile rows g, g+1, g+2: bounds over the 8 lanes of the word
+    if (y0 + 4 * g < H) {
+      float mn = fminf(fminf(mnA, mnB), mnC), mx = fmaxf(fmaxf(mxA, mxB), mxC);
+#pragma unroll
+      for (int o = 1; o < 8; o <<= 1) {
+        mn = fminf(mn, __shfl_xor_sync(amask, mn, o));
+        mx = fmaxf(mx, __shfl_xor_sync(amask, mx, o));
+      }
+      if ((lane & 7) == 0) {
+        a.tmin[bbase + (size_t)g * a.wpr] = mn;
+        a.tmax[bbase + (size_t)g * a.wpr] = mx;
+      }
+    }
+    mnA = mnB; mxA = mxB; mnB = mnC; mxB = mxC;
+    const int y = y0 + 4 * g + 2;
+    emit(y, 0.875f, 0.125f, hA, hB);
+    emit(y + 1, 0.625f, 0.375f, hA, hB);
+    if (g + 1 < RB / 4) {
+      emit(y + 2, 0.375f, 0.625f, hA, hB);
+      emit(y + 3, 0.125f, 0.875f, hA, hB);
+    }
+  }
+}
+
 template <int E, int NW>
 __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -211,93 +382,7 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   }
   __syncthreads();
   // ---------------- phase 0b: tags, x4 taps (results.py:229-230) ------------------------------------
-  if (active) {
-    const int q = X0 >> 2;                       // this lane's quarter-res column
-    const int tb = q - 1 - txo;                  // index of T[q-1] in a tile row
-    const bool x_first = (q == 0);
-    // columns 4q+{0,1}: taps (q-1,q) weights (.375,.625),(.125,.875); 4q+{2,3}: (q,q+1) (.875,.125),(.625,.375)
-    const float wa0 = x_first ? 1.f : 0.375f, wb0 = x_first ? 0.f : 0.625f;
-    const float wa1 = x_first ? 1.f : 0.125f, wb1 = x_first ? 0.f : 0.875f;
-    float hA[E][4], hB[E][4];
-    // also returns the range of the sources of the FIRST tag component: every output it contributes to
-    // is a convex combination of them (refine prefilter, tag_bmin / tag_bmax)
-    auto hpass = [&](int r, float (&h)[E][4], float& mn, float& mx) {
-#pragma unroll
-      for (int e = 0; e < E; ++e) {
-        const float* t = sT + e * TR * tc + r * tc + tb;
-        const float t0 = t[0], t1 = t[1], t2 = t[2];
-        if (e == 0) { mn = fminf(fminf(t0, t1), t2); mx = fmaxf(fmaxf(t0, t1), t2); }
-        const float a0 = x_first ? t1 : t0, b0 = x_first ? t2 : t1;
-        h[e][0] = fmaf(wa0, a0, __fmul_rn(wb0, b0));
-        h[e][1] = fmaf(wa1, a0, __fmul_rn(wb1, b0));
-        h[e][2] = fmaf(0.875f, t1, __fmul_rn(0.125f, t2));
-        h[e][3] = fmaf(0.625f, t1, __fmul_rn(0.375f, t2));
-      }
-    };
-    float* tg_plane = a.agg_tags + ((size_t)b * a.K + k) * H * W * E;
-    auto emit = [&](int y, float wy0, float wy1, const float (&A)[E][4], const float (&Bv)[E][4]) {
-      if (y < y0 || y >= y0 + RB || y >= H) return;
-      float o[E][4];
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) o[e][c] = fmaf(wy0, A[e][c], __fmul_rn(wy1, Bv[e][c]));
-      float* dst = tg_plane + ((size_t)y * W + X0) * E;
-      if (E == 1) {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[0][1], o[0][2], o[0][3]);
-      } else {
-        *reinterpret_cast<float4*>(dst) = make_float4(o[0][0], o[E - 1][0], o[0][1], o[E - 1][1]);
-        *reinterpret_cast<float4*>(dst + 4) = make_float4(o[0][2], o[E - 1][2], o[0][3], o[E - 1][3]);
-      }
-    };
-    // tile rows: r <-> quarter-res row tyo + r = y0/4 - 1 + r.  Rows y0, y0+1 use (i-1, i) with
-    // i = y0/4, i.e. tile rows (0, 1); then each group of 4 rows 4i+2..4i+5 uses rows (i, i+1).
-    const unsigned amask = __activemask();      // W % 32 == 0: whole 8-lane word groups are active
-    float mnA, mxA, mnB, mxB, mnC, mxC;
-    hpass(0, hA, mnA, mxA);
-    hpass(1, hB, mnB, mxB);
-    if (y0 == 0) {          // first two rows of the image: src clamps to 0 -> taps (row 0, row 1), weights (1, 0)
-      float hC[E][4];
-      hpass(2, hC, mnC, mxC);   // tile row 1 = image row 0, tile row 2 = image row 1
-      emit(0, 1.f, 0.f, hB, hC);
-      emit(1, 1.f, 0.f, hB, hC);
-    } else {
-      emit(y0, 0.375f, 0.625f, hA, hB);
-      emit(y0 + 1, 0.125f, 0.875f, hA, hB);
-    }
-    const int HB = (H + 3) >> 2;
-    const size_t bbase = (((size_t)b * a.K + k) * HB + (y0 >> 2)) * a.wpr + (X0 >> 5);
-#pragma unroll 1
-    for (int g = 0; g < RB / 4; ++g) {
-      // rows y0 + 4g + 2 .. y0 + 4g + 5 : taps (tile row g+1, tile row g+2)
-#pragma unroll
-      for (int e = 0; e < E; ++e)
-#pragma unroll
-        for (int c = 0; c < 4; ++c) hA[e][c] = hB[e][c];
-      hpass(g + 2, hB, mnC, mxC);
-      // band of rows y0+4g .. y0+4g+3 reads tile rows g, g+1, g+2: bounds over the 8 lanes of the word
-      if (y0 + 4 * g < H) {
-        float mn = fminf(fminf(mnA, mnB), mnC), mx = fmaxf(fmaxf(mxA, mxB), mxC);
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          mn = fminf(mn, __shfl_xor_sync(amask, mn, o));
-          mx = fmaxf(mx, __shfl_xor_sync(amask, mx, o));
-        }
-        if ((lane & 7) == 0) {
-          a.tmin[bbase + (size_t)g * a.wpr] = mn;
-          a.tmax[bbase + (size_t)g * a.wpr] = mx;
-        }
-      }
-      mnA = mnB; mxA = mxB; mnB = mnC; mxB = mxC;
-      const int y = y0 + 4 * g + 2;
-      emit(y, 0.875f, 0.125f, hA, hB);
-      emit(y + 1, 0.625f, 0.375f, hA, hB);
-      if (g + 1 < RB / 4) {
-        emit(y + 2, 0.375f, 0.625f, hA, hB);
-        emit(y + 3, 0.125f, 0.875f, hA, hB);
-      }
-    }
-  }
+  if (active) tags_x4_band<E, RB, TR>(a, sT, tc, txo, X0, y0, b, k, lane);
   __syncthreads();   // every warp is done with the tag tiles before the half-res tile overwrites them
 
   // ---------------- phase 1: stage the heatmap inputs -------------------------------------------------
@@ -418,62 +503,9 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
     float hA[4], hB[4], hC[4], hD[4];
     hpass(0, hA);
     hpass(1, hB);
-    // register windows: r0..r3 = row maxima of rows y-4..y-1, vq0 / vq1 = values of rows y-2 / y-1
-    float r0[4], r1[4], r2[4], r3[4], vq0[4], vq1[4];
-#pragma unroll
-    for (int c = 0; c < 4; ++c) { r0[c] = r1[c] = r2[c] = r3[c] = NINF; vq0[c] = vq1[c] = NINF; }
-    float* const hm_plane = a.agg_hm + ((size_t)b * a.K + k) * H * W + X0;
-    const size_t wbase = ((size_t)b * a.K + k) * H * a.wpr + (X0 >> 5);
-    const bool word_writer = active && (lane & 7) == 0;
-    const int shl = 4 * (lane & 7);
-
-    // t = index of the row in the walk (row y = ys + t); rows outside the image carry -inf
-    auto process_row = [&](int t, const float (&v)[4]) {
-      const int y = ys + t;
-      if (t >= 2 && t < RB + 2 && y < H && active)
-        *reinterpret_cast<float4*>(hm_plane + (size_t)y * W) = make_float4(v[0], v[1], v[2], v[3]);
-      // 5-wide row maximum: own 4 + 2 from each neighbour lane (halo columns for lanes 0 / 31)
-      float l2 = __shfl_up_sync(kFull, v[2], 1), l3 = __shfl_up_sync(kFull, v[3], 1);
-      float q0 = __shfl_down_sync(kFull, v[0], 1), q1 = __shfl_down_sync(kFull, v[1], 1);
-      if (lane == 0) { const float2 e = *reinterpret_cast<const float2*>(edge + t * 4); l2 = e.x; l3 = e.y; }
-      if (lane == 31) { const float2 e = *reinterpret_cast<const float2*>(edge + t * 4 + 2); q0 = e.x; q1 = e.y; }
-      const float pb = fmaxf(v[0], v[1]), pc = fmaxf(v[2], v[3]);
-      float rm[4];
-      rm[0] = max3(fmaxf(l2, l3), pb, v[2]);
-      rm[1] = max3(l3, pb, pc);
-      rm[2] = max3(pb, pc, q0);
-      rm[3] = max3(v[1], pc, fmaxf(q0, q1));
-      // centre row yc = y - 2: 5-tall column maximum over rows y-4..y
-      const int yc = y - 2;
-      if (t >= 4 && yc < H) {   // uniform over the CTA
-        const float m0 = max3(max3(r0[0], r1[0], r2[0]), r3[0], rm[0]);
-        const float m1 = max3(max3(r0[1], r1[1], r2[1]), r3[1], rm[1]);
-        const float m2 = max3(max3(r0[2], r1[2], r2[2]), r3[2], rm[2]);
-        const float m3 = max3(max3(r0[3], r1[3], r2[3]), r3[3], rm[3]);
-        const bool k0 = (m0 == vq0[0]), k1 = (m1 == vq0[1]), k2 = (m2 == vq0[2]), k3 = (m3 == vq0[3]);
-        // NMS'd value of a suppressed pixel is +-0; its sign cannot change any comparison made on the word maximum
-        float wm4 = fmaxf(fmaxf(k0 ? vq0[0] : 0.f, k1 ? vq0[1] : 0.f), fmaxf(k2 ? vq0[2] : 0.f, k3 ? vq0[3] : 0.f));
-        float hm4 = fmaxf(fmaxf(vq0[0], vq0[1]), fmaxf(vq0[2], vq0[3]));
-        unsigned bits = ((k0 ? 1u : 0u) | (k1 ? 2u : 0u) | (k2 ? 4u : 0u) | (k3 ? 8u : 0u)) << shl;
-#pragma unroll
-        for (int o = 1; o < 8; o <<= 1) {
-          bits |= __shfl_xor_sync(kFull, bits, o);
-          hm4 = fmaxf(hm4, __shfl_xor_sync(kFull, hm4, o));
-          wm4 = fmaxf(wm4, __shfl_xor_sync(kFull, wm4, o));
-        }
-        if (word_writer) {
-          const size_t w = wbase + (size_t)yc * a.wpr;
-          a.mask[w] = bits;
-          a.wmax[w] = wm4;
-          a.hmax[w] = hm4;
-        }
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        r0[c] = r1[c]; r1[c] = r2[c]; r2[c] = r3[c]; r3[c] = rm[c];
-        vq0[c] = vq1[c]; vq1[c] = v[c];
-      }
-    };
+    NmsColumnWalk<RB> nms;
+    nms.init(a, b, k, X0, ys, edge, active, lane);
+    auto process_row = [&](int t, const float (&v)[4]) { nms.row(a, t, v); };
 
 #pragma unroll 1
     for (int it = 0; it < NROWS / 4; ++it) {
