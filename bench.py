@@ -387,7 +387,7 @@ def main():
     ap.add_argument("--split-priority", action="store_true")
     ap.add_argument("--inputs", default="hrnet", choices=["hrnet", "netlike", "crowd"],
                     help="hrnet: outputs of a default-init HigherHRNet-W32 on seeded random images; netlike: CPU-generated fields")
-    ap.add_argument("--streams", type=int, default=4, help="batches in flight per GPU (1 = strictly sequential)")
+    ap.add_argument("--streams", type=int, default=8, help="batches in flight per GPU (1 = strictly sequential)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
