@@ -74,8 +74,9 @@ typedef struct HpdParams {
   int32_t tags_preflipped; /* 1: tag_f is already un-flipped and joint-permuted, i.e. it is the second entry of
                             * the reference's tags_heatmaps list (model.py:91-94) as from_preds receives it */
   int32_t force_generic; /* testing only, 0 in production.  bit 0: generic aggregation kernel instead of the specialised
-                          * ones, and the exact heap instead of the sorted-register fast path in top-k; bit 1: one warp
-                          * per row in top-k even for small batches.  All variants are bit-identical (tests). */
+                          * ones, and in top-k the literal libstdc++ heap code (one lane, shared memory) over the whole
+                          * row instead of the floor mode / warp-wide heap; bit 1: one warp per row in top-k even for
+                          * small batches.  All variants are bit-identical (tests). */
   double det_thr;       /* grouping.py:71,100  (compared in float64) */
   double tag_thr;       /* grouping.py:72,135  (compared in float64) */
   int32_t flip_index[HPD_MAX_KPTS];   /* COCO_FLIP_INDEX (transforms.py:11) */

@@ -6,14 +6,18 @@
 // __sort_heap: a k-entry heap whose top is the smallest kept value, fed by the stream in index
 // order; an element enters only if it is STRICTLY greater than the current top.  Among equal
 // values the final order is therefore a function of the heap's history, not of the indices
-// (SURVEY.md App. A.4).  This kernel replays that history exactly:
-//   * one warp per (image, joint) row; the heap lives in shared memory and is edited by lane 0
-//     with the libstdc++ __adjust_heap / __push_heap control flow;
-//   * the heap top never decreases, so the stream is pre-filtered 32 words (1024 pixels) at a
-//     time with the per-word maximum of the NMS'd values written by the aggregation kernel;
-//     only words that can still contain an entering element are expanded (one coalesced 128-byte
-//     line of the heatmap + the survivor mask word), and entering elements are replayed in index
-//     order with the live top.
+// (SURVEY.md App. A.4).  Per (image, joint) row:
+//   * the heap top never decreases, so the row is streamed through the per-word maxima of the NMS'd
+//     values written by the aggregation kernel (32 words = 1024 pixels per step); only words that can
+//     still contain an entering element are expanded (one coalesced 128-byte line of the heatmap + the
+//     survivor mask word, up to 8 words per batch of loads);
+//   * floor mode: the word maxima also give a lower bound of the M-th largest value before the row is
+//     streamed; a sorted-across-the-lanes sink started at that floor yields the M largest values, which is
+//     the answer whenever it is free of ties;
+//   * otherwise the heap history is replayed exactly: the libstdc++ heap with slot i in lane i
+//     (WarpHeap), or -- force_generic bit 0 -- the literal __adjust_heap / __push_heap code run by lane 0
+//     on shared memory (HeapSink), kept as the anchor the other two are tested against.
+// One warp per row (topk_kernel) or, for small batches, 8 warps per row (topk_split_kernel).
 // The NMS'd value of a suppressed pixel is x*0 (sign of x): zeros do enter while the top is
 // negative and their indices are part of the bit-exact contract.
 #include "common.cuh"
