@@ -95,3 +95,17 @@ def test_back_projection_and_coco_records():
     assert len(recs[0]["keypoints"]) == 51 and recs[0]["keypoints"][2] == 1 and abs(recs[0]["keypoints"][0] - 100.0) < 1e-3
     assert recs[1]["score"] == 0.25
     assert coco_records(1, np.zeros((0, 17, 2)), np.zeros((0,))) == []
+
+
+def test_division_by_three_as_two_fmas_is_the_ieee_quotient(tmp_path):
+    """csrc/aggregate_nms_ms.cuh divides the 3-scale sum by 3 with two FMAs around RN(1/3); tools/check_div3.c
+    compares that with x / 3.0f bit for bit (here: every mantissa and sign in four binades; --full = all 2^32)."""
+    import shutil
+    import subprocess
+    cc = shutil.which("gcc") or shutil.which("cc")
+    exe = str(tmp_path / "check_div3")
+    src = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools", "check_div3.c")
+    subprocess.run([cc, "-O2", "-ffp-contract=off", "-o", exe, src, "-lm"], check=True)
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stdout
+    assert " 0 mismatches" in r.stdout
