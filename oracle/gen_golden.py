@@ -1,7 +1,7 @@
 """TEST INFRASTRUCTURE ONLY -- regenerates tests/golden/*.npz by running the UNMODIFIED reference
 (/root/reference, build container only) on the seeded synthetic inputs of oracle/golden_cases.py.
 
-    python oracle/gen_golden.py
+    python oracle/gen_golden.py [case ...]
 
 Each file stores what the reference produced: top-k indices/scores/coords/tags, match_by_tag output,
 final (grouped_joints, person_scores) and SHA-256 digests of the aggregated heatmaps, tag maps and
@@ -30,7 +30,13 @@ def main():
     os.makedirs(out_dir, exist_ok=True)
     manifest = {"torch": torch.__version__, "numpy": np.__version__, "reference": "thawro/pytorch-human-pose @ /root/reference",
                 "munkres": "restated 1.1.4 (oracle/refshim/munkres.py) -- parity unpinned", "cases": {}}
+    only = set(sys.argv[1:])                       # optional: regenerate just these cases
+    man_path = os.path.join(out_dir, "MANIFEST.json")
+    if only and os.path.isfile(man_path):
+        manifest["cases"] = json.load(open(man_path))["cases"]
     for name in golden_cases.CASES:
+        if only and name not in only:
+            continue
         scales, size, M, det, tthr = golden_cases.make_inputs(name)
         img = synth.image_slice(scales, 0)
         hm, tg = ref_runner.aggregate_torch(img, (size, size))

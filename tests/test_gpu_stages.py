@@ -153,7 +153,8 @@ def test_from_preds_and_fallback_dtype(oracle):
 
 
 @pytest.mark.parametrize("name", ["netlike192_flip", "crowd256_q_flip", "crowd256_val_m20", "empty256_fallback",
-                                  "crowd512_30_flip", "netlike512_flip"])
+                                  "crowd512_30_flip", "netlike512_flip", "crowd256_m5", "crowd256_m32",
+                                  "crowd256_tight_thr", "netlike256_some_negative", "crowd192_q_dense"])
 def test_decode_matches_committed_reference_goldens(name):
     """The CUDA path against tests/golden/*.npz -- outputs of the UNMODIFIED reference, no oracle in between."""
     from hpdecode import BottomUpDecoder
