@@ -221,3 +221,67 @@ def test_ballot_adjust_heap_equals_libstdcxx_adjust_heap():
             b_v[last], b_i[last] = b_v[0], b_i[0]
             adjust_heap_ballots(b_v, b_i, 0, last, val_b, idx_b)
             assert a_v == b_v and a_i == b_i
+
+
+# ------------------------------------------------------------------------------------------------------
+# 3. the exact path as a log replay (what the kernels do for rows with ties; DESIGN 7b builds on it)
+# ------------------------------------------------------------------------------------------------------
+def entering_log(row, M, begin, end, seed_values):
+    """Elements of [begin, end) that enter the sequential heap, given the M largest VALUES seen before `begin`
+    (whether an element enters depends only on the M-th largest value before it, not on the heap's shape)."""
+    kept = sorted(seed_values, reverse=True)
+    log = []
+    for t in range(begin, end):
+        if row[t] > kept[-1]:
+            log.append(t)
+            kept.append(row[t])
+            kept.sort(reverse=True)
+            kept.pop()
+    return log, kept
+
+
+def replay(row, M, log):
+    """std::partial_sort's heap: make_heap on the first M elements, __adjust_heap(0, M, x) per entering x,
+    sort_heap -- using the literal functions above."""
+    v = [float(x) for x in row[:M]]
+    i = list(range(M))
+    for parent in range((M - 2) // 2, -1, -1):
+        adjust_heap_literal(v, i, parent, M, v[parent], i[parent])
+    for t in log:
+        assert row[t] > v[0]
+        adjust_heap_literal(v, i, 0, M, float(row[t]), t)
+    for last in range(M - 1, 0, -1):
+        val, idx = v[last], i[last]
+        v[last], i[last] = v[0], i[0]
+        adjust_heap_literal(v, i, 0, last, val, idx)
+    return np.array(v, np.float32), np.array(i, np.int32)
+
+
+@pytest.mark.parametrize("levels,segments", [(4, 1), (16, 8), (1000, 8), (16, 5)])
+def test_segmented_logs_replayed_through_the_heap_give_the_reference_order(levels, segments, oracle):
+    """Tie-heavy rows: the log of entering elements, produced per segment from the top-M values of the
+    segment's prefix, replayed through the libstdc++ heap, is bit-for-bit torch's / the oracle's top-k."""
+    rng = np.random.default_rng(levels + segments)
+    K, H, W, M = 24, 64, 64, 30
+    N = H * W
+    rows = np.zeros((K, N), np.float32)
+    for k in range(K):
+        n = int(rng.integers(5, 600))
+        pos = rng.choice(N, n, replace=False)
+        rows[k, pos] = rng.integers(-levels, levels + 1, n).astype(np.float32) / np.float32(levels)
+    _, _, scores, idx = oracle.top_k(rows.reshape(K, H, W), np.zeros((K, H, W, 1), np.float32), M)
+    for k in range(K):
+        row = rows[k]
+        # geometric segment bounds: the entries thin out like 1/t
+        bounds = [M] + [max(M, N >> (segments - s)) for s in range(1, segments)] + [N]
+        bounds = sorted(set(bounds))
+        log = []
+        for a, b in zip(bounds[:-1], bounds[1:]):
+            seed = np.sort(row[:a])[::-1][:M].tolist()          # top-M values of the prefix, any order of ties
+            seg_log, _ = entering_log(row, M, a, b, seed)
+            log.extend(seg_log)
+        whole, _ = entering_log(row, M, M, N, row[:M].tolist())
+        assert log == whole                                     # segments find exactly the sequential entries
+        got_v, got_i = replay(row, M, log)
+        assert np.array_equal(got_i, idx[k])
+        assert np.array_equal(got_v.view(np.uint32), scores[k].view(np.uint32))
