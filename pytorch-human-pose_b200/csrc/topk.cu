@@ -439,7 +439,7 @@ __device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ h
   scan_range(sink, hm, mk, wm, W, wpr, 0, H * wpr, M, lane);
 }
 
-__global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __restrict__ agg_hm,
+__global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* __restrict__ agg_hm,
                                                               const float* __restrict__ agg_tags,
                                                               const uint32_t* __restrict__ mask,
                                                               const float* __restrict__ wmax, int rows, int H, int W,
@@ -519,7 +519,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32) topk_kernel(const float* __re
 constexpr int kSplitWarps = 8;
 constexpr int kSegLogCap = 320;
 
-__global__ void __launch_bounds__(kSplitWarps * 32) topk_split_kernel(const float* __restrict__ agg_hm,
+__global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_split_kernel(const float* __restrict__ agg_hm,
                                                                      const float* __restrict__ agg_tags,
                                                                      const uint32_t* __restrict__ mask,
                                                                      const float* __restrict__ wmax, int H, int W,
