@@ -281,6 +281,50 @@ def run_ours(args):
     def value_step():
         pipe.submit([resident], (S, S), after_tail=finish)
 
+    def parity_check():
+        """Before anything is timed: decode this rank's batch once and compare images of it with the CPU oracle
+        (bit-exact grouped joints and person scores); at N > 1 rank 0 also compares every rank's gathered rows
+        with a checksum the owning rank computed locally."""
+        import hashlib
+        from oracle import cpu_oracle      # the checker, never the thing measured
+        res = dec.decode([resident], (S, S), slot=NS)
+        packed = res.packed()
+        rows = packed.cpu().numpy()
+        out = DecodeResult.unpack(rows, MAX_PEOPLE, K_JOINTS, 2)
+        n_check = min(max(1, 8 // world), len(host["hm_lo"]), B)
+        ok = True
+        for b in range(n_check):
+            hm_o, tg_o = cpu_oracle.aggregate([{k: v[b] for k, v in host.items()}], (S, S))
+            ref = cpu_oracle.parse(hm_o, tg_o, MAX_PEOPLE, DET_THR, TAG_THR)
+            gj, ps = out[b]
+            ok = ok and gj.shape == ref["grouped_joints"].shape and \
+                np.array_equal(np.asarray(gj, np.float32).view(np.uint32), ref["grouped_joints"].view(np.uint32)) and \
+                np.array_equal(np.asarray(ps, np.float32).view(np.uint32), ref["person_scores"].view(np.uint32))
+        info = {"checked": n_check * world, "ok": bool(ok), "against": "oracle/hpd_oracle.cpp (grouped joints + person scores, bit-exact)"}
+        if world > 1:
+            digest = torch.frombuffer(bytearray(hashlib.sha256(rows.tobytes()).digest()), dtype=torch.uint8).to(dev)
+            digests = [torch.empty_like(digest) for _ in range(world)]
+            dist.all_gather(digests, digest)
+            flag = torch.tensor([int(ok)], device=dev)
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            gathered = torch.empty((world * B, F), device=dev) if rank == 0 else None
+            gather_packed_equal(packed, gathered, dst=0)
+            info["ok"] = bool(flag.item())
+            if rank == 0:
+                g = gathered.cpu().numpy()
+                same = [hashlib.sha256(g[r * B:(r + 1) * B].tobytes()).digest() == bytes(digests[r].cpu().tolist())
+                        for r in range(world)]
+                info["gathered_rows_match_rank_checksums"] = bool(all(same))
+                info["ok"] = info["ok"] and all(same)
+        return info
+
+    parity = parity_check()
+    if rank == 0 and not parity["ok"]:
+        print(json.dumps({"metric": METRIC, "error": "parity check against the oracle FAILED; nothing was timed", "parity": parity}),
+              flush=True)
+    if not parity["ok"]:
+        raise SystemExit(3)
+
     # ---- value: inputs resident in HBM -------------------------------------------------------------
     run_steps(max(args.warmup, 3) * NS, value_step)
     if sampler:
@@ -359,7 +403,7 @@ def run_ours(args):
             "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
                     "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in pinned.values())) * world,
                     "d2h_bytes_per_step": int(B * F * 4), "steps": e2e_steps},
-            "gpu_launches": launches, "clocks": clocks,
+            "gpu_launches": launches, "clocks": clocks, "parity": parity,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = min(host_cores(), 32)

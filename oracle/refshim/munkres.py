@@ -7,7 +7,8 @@ vendored in the reference and cannot be installed here (no network), so this
 module restates the *published* algorithm of ``Munkres.compute`` from memory of
 the 1.1.x sources.  PARITY UNPINNED: no genuine munkres wheel was available to
 diff against; the optimal cost is cross-checked against
-``scipy.optimize.linear_sum_assignment`` in tests/test_oracle_munkres.py.
+``scipy.optimize.linear_sum_assignment`` in tests/test_oracle.py
+(``test_munkres_*``).
 
 Only what the reference uses is provided: ``Munkres().compute(matrix)`` on a
 rows<=cols float64 numpy matrix.  The two places whose exact shape decides the

@@ -528,8 +528,7 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
       const dim3 grid((a.W + 128 * NW - 1) / (128 * NW), (a.H + x2::RB - 1) / x2::RB, a.B * a.K);
 #define HPD_X2_LAUNCH(E_, NW_)                                                                              \
   do {                                                                                                      \
-    if (smem > 48 * 1024)                                                                                   \
-      cudaFuncSetAttribute(x2::agg_nms_x2_kernel<E_, NW_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (int rc_ = ensure_dynamic_smem((const void*)x2::agg_nms_x2_kernel<E_, NW_>, smem, "agg_nms_x2_kernel")) return rc_; \
     x2::agg_nms_x2_kernel<E_, NW_><<<grid, 32 * NW_, smem, st>>>(a);                                        \
   } while (0)
       if (a.E == 1) { if (NW == 4) HPD_X2_LAUNCH(1, 4); else if (NW == 2) HPD_X2_LAUNCH(1, 2); else HPD_X2_LAUNCH(1, 1); }
@@ -586,8 +585,7 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
         const dim3 grid((a.W + 128 * NW - 1) / (128 * NW), (a.H + ms::RB - 1) / ms::RB, a.B * a.K);
 #define HPD_MS_LAUNCH(E_, NW_, NS_)                                                                              \
   do {                                                                                                           \
-    if (smem > 48 * 1024)                                                                                        \
-      cudaFuncSetAttribute(ms::agg_nms_ms_kernel<E_, NW_, NS_>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+    if (int rc_ = ensure_dynamic_smem((const void*)ms::agg_nms_ms_kernel<E_, NW_, NS_>, smem, "agg_nms_ms_kernel")) return rc_; \
     ms::agg_nms_ms_kernel<E_, NW_, NS_><<<grid, 32 * NW_, smem, st>>>(a, g);                                     \
   } while (0)
 #define HPD_MS_NS(E_, NW_)                                                                                       \
@@ -610,10 +608,7 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
     set_error("resize ratios need %zu bytes of shared memory per tile (> 227 KB)", smem);
     return HPD_EINVAL;
   }
-  if (smem > 48 * 1024) {
-    if (cudaFuncSetAttribute(agg_nms_generic_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess)
-      return check_launch("cudaFuncSetAttribute(agg_nms_generic_kernel)");
-  }
+  if (int rc = ensure_dynamic_smem((const void*)agg_nms_generic_kernel, smem, "agg_nms_generic_kernel")) return rc;
   const dim3 grid((a.W + TW - 1) / TW, (a.H + TH - 1) / TH, a.B * a.K);
   agg_nms_generic_kernel<<<grid, kAggThreads, smem, st>>>(a);
   count_launch();

@@ -4,6 +4,10 @@
 #include <stdio.h>
 #include <string.h>
 
+#include <map>
+#include <mutex>
+#include <utility>
+
 #include "common.cuh"
 
 namespace hpd {
@@ -23,11 +27,36 @@ void set_error(const char* fmt, ...) {
 void count_launch(int n) { g_launches += n; }
 
 int check_launch(const char* what) {
-  const cudaError_t e = cudaPeekAtLastError();
+  const cudaError_t e = cudaGetLastError();   // consumes the error: a failed launch must not poison later calls
   if (e != cudaSuccess) {
     set_error("%s: %s", what, cudaGetErrorString(e));
     return HPD_ECUDA;
   }
+  return HPD_OK;
+}
+
+// Kernels that need more than 48 KB of dynamic shared memory opt in once per (kernel, device): the
+// attribute is sticky, so it is not set again on every launch, and a refusal is reported.
+int ensure_dynamic_smem(const void* kernel, size_t bytes, const char* name) {
+  if (bytes <= 48 * 1024) return HPD_OK;
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: no current CUDA device", name);
+    return HPD_ECUDA;
+  }
+  static std::mutex mu;
+  static std::map<std::pair<const void*, int>, size_t> granted;
+  std::lock_guard<std::mutex> lock(mu);
+  size_t& have = granted[std::make_pair(kernel, dev)];
+  if (have >= bytes) return HPD_OK;
+  const cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    set_error("%s: cannot opt in to %zu bytes of shared memory: %s", name, bytes, cudaGetErrorString(e));
+    return HPD_ECUDA;
+  }
+  have = bytes;
   return HPD_OK;
 }
 

@@ -16,6 +16,7 @@ constexpr unsigned kFull = 0xffffffffu;
 void set_error(const char* fmt, ...);
 void count_launch(int n = 1);
 int check_launch(const char* what);
+int ensure_dynamic_smem(const void* kernel, size_t bytes, const char* name);
 
 // ---- bilinear taps, torch CPU semantics (results.py:51,59,65; aten UpSampleKernel.cpp) -----
 struct Tap {

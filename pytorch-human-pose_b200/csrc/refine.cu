@@ -74,8 +74,10 @@ __device__ __forceinline__ void quarter_offset(const float* __restrict__ m, int 
   y += (m[(size_t)min(yi + 1, H - 1) * W + xi] > m[(size_t)max(yi - 1, 0) * W + xi]) ? 0.25f : -0.25f;
 }
 
-// one warp per person, one block per image
-__global__ void adjust_prepare_kernel(const float* __restrict__ agg_hm, const float* __restrict__ agg_tags,
+// one warp per person, one block per image.  Coordinates come from the top-k stage inside hpd_decode and are
+// always inside the map; the standalone adjust / refine twins receive caller-supplied coordinates, which are
+// clamped to the map before any read (the Python wrappers reject them where the reference would raise).
+__global__ void __launch_bounds__(32 * HPD_MAX_PEOPLE) adjust_prepare_kernel(const float* __restrict__ agg_hm, const float* __restrict__ agg_tags,
                                       const int32_t* __restrict__ idx_k, const int32_t* __restrict__ n_person, int K,
                                       int M, int E, int H, int W, int do_adjust, int do_refine,
                                       float* __restrict__ poses, float* __restrict__ person_scores, RefineWs ws) {
@@ -98,7 +100,7 @@ __global__ void adjust_prepare_kernel(const float* __restrict__ agg_hm, const fl
     if (lane < K) {
       x = d[0]; y = d[1]; score = d[2];
       if (do_adjust && score != 0.f) {   // grouping.py:172-191
-        const int xi = (int)x, yi = (int)y;
+        const int xi = min(max((int)x, 0), W - 1), yi = min(max((int)y, 0), H - 1);
         quarter_offset(hm_b + (size_t)lane * H * W, H, W, xi, yi, x, y);
         x += 0.5f; y += 0.5f;
         d[0] = x; d[1] = y;
@@ -110,7 +112,7 @@ __global__ void adjust_prepare_kernel(const float* __restrict__ agg_hm, const fl
     const unsigned hmask = __ballot_sync(kFull, has);
     if (has && do_refine) {
       const int pos = __popc(hmask & ((1u << lane) - 1u));
-      const int xi = (int)x, yi = (int)y;
+      const int xi = min(max((int)x, 0), W - 1), yi = min(max((int)y, 0), H - 1);
       const float* t = tg_b + (((size_t)lane * H + yi) * W + xi) * E;
       s_tl[p][pos][0] = t[0];
       s_tl[p][pos][1] = (E > 1) ? t[1] : 0.f;

@@ -8,6 +8,7 @@ copied to the host until ``DecodeResult.to_numpy()`` is called, and then only th
 The reference decodes one image per call (results.py:233-234 strips the batch dim); here the
 batch is a superset: image b of a batch gives exactly what the reference returns for that image.
 """
+from collections import OrderedDict
 from typing import List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -65,7 +66,7 @@ def _finish(poses: np.ndarray, scores: np.ndarray, fallback: int):
 
 class BottomUpDecoder:
     def __init__(self, num_kpts: int = 17, max_num_people: int = 30, det_thr: float = 0.05, tag_thr: float = 0.5,
-                 device="cuda:0", adjust: bool = True, refine: bool = True):
+                 device="cuda:0", adjust: bool = True, refine: bool = True, max_cached_shapes: int = 4):
         if not torch.cuda.is_available():
             raise ops._lib.HpdError("hpdecode needs a CUDA device (sm_100a); there is no CPU fallback")
         ops._lib.lib()
@@ -73,18 +74,34 @@ class BottomUpDecoder:
         self.det_thr, self.tag_thr = det_thr, tag_thr
         self.adjust, self.refine = adjust, refine
         self.device = torch.device(device)
-        self._bufs = {}
+        self._bufs = OrderedDict()
+        self.max_cached_shapes = max_cached_shapes
 
     def buffers(self, B, H, W, E, slot=0) -> ops.DecodeBuffers:
-        key = (B, H, W, E, slot)
-        if key not in self._bufs:
-            self._bufs[key] = ops.DecodeBuffers(B, self.num_kpts, H, W, E, self.max_num_people, self.device)
-        return self._bufs[key]
+        """Buffer set for one (shape, slot), kept in a small LRU: bottom-up inference sees many padded
+        (H, W) (resize_align_multi_scale keeps the aspect ratio) and a set is ~80 MB per image at 512-class
+        sizes, so at most ``max_cached_shapes`` distinct shapes stay resident (slots of one shape are evicted
+        together; an evicted set is freed once the stream work that uses it has run, by the caching allocator)."""
+        shape = (B, H, W, E)
+        slots = self._bufs.get(shape)
+        if slots is None:
+            while len(self._bufs) >= self.max_cached_shapes:
+                self._bufs.popitem(last=False)
+            slots = self._bufs[shape] = {}
+        else:
+            self._bufs.move_to_end(shape)
+        if slot not in slots:
+            slots[slot] = ops.DecodeBuffers(B, self.num_kpts, H, W, E, self.max_num_people, self.device)
+        return slots[slot]
 
     def decode(self, scales: Sequence[dict], out_hw: Tuple[int, int], tag_scale: int = 0,
                tags_preflipped: bool = False, slot: int = 0) -> DecodeResult:
         """scales: one dict per test scale with CUDA float32 tensors hm_lo, hm_hi, tag [B,K,h,w] and,
-        for the flip test, hm_lo_f, hm_hi_f, tag_f (raw outputs of the flipped forward)."""
+        for the flip test, hm_lo_f, hm_hi_f, tag_f (raw outputs of the flipped forward).
+
+        The returned DecodeResult VIEWS the decoder's cached buffer set for this (shape, slot): it is
+        overwritten by the next decode of the same shape and slot.  Read it (``to_numpy()``), ``clone()``
+        what must outlive that, or pass distinct ``slot`` values for results that are held together."""
         H, W = out_hw
         B = scales[0]["hm_lo"].shape[0]
         E = 2 if scales[tag_scale].get("tag_f") is not None else 1
@@ -115,6 +132,8 @@ class DecodePipeline:
     batch i+1's aggregation overlaps batch i's tail and the small kernels get SM slots as soon as
     they are runnable.  ``submit`` returns the lane's DecodeResult; it stays valid until the lane is
     reused ``depth`` submits later (call ``result.ready.synchronize()`` or ``drain()`` before reading).
+    Lifetime contract for the inputs: ``submit`` records their use on the lane's stream
+    (``Tensor.record_stream``), so the caller may drop them as soon as it returns.
     """
 
     def __init__(self, decoder: "BottomUpDecoder", depth: int = 3, split_priority: bool = False):
@@ -146,11 +165,18 @@ class DecodePipeline:
                                  len(scales), tag_scale)
         cur = torch.cuda.current_stream(d.device)
         ln["s_agg"].wait_stream(cur)
+        # The inputs were allocated on the caller's stream but are read on the lane's: tell the caching
+        # allocator, or a caller that drops them right after submit() (net outputs -> submit -> next forward)
+        # could get their memory back while the aggregation kernel is still reading it.
+        for s in scales:
+            for t in s.values():
+                if t is not None and t.is_cuda:
+                    t.record_stream(ln["s_agg"])
         with torch.cuda.stream(ln["s_agg"]):
             if ln["used"]:
                 ln["s_agg"].wait_event(ln["ready"])     # the lane's previous batch has been consumed
             if before_agg is not None:
-                scales = before_agg(ln) or scales
+                scales = before_agg(ln) or scales      # tensors made here belong to the lane's stream already
             ops.run_stage("aggregate_nms", bufs, params, scales=scales)
             if ln["s_tail"] is not ln["s_agg"]:
                 ln["agg_done"].record()

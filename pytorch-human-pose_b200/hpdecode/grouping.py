@@ -75,6 +75,10 @@ class MPPEHeatmapParser(object):
         ops.run_stage("nms", bufs, params)
         ops.run_stage("topk", bufs, params)
         P = grouped.shape[0]
+        det = grouped[..., 2] != 0
+        if det.any() and not ((grouped[..., 0][det] >= 0).all() and (grouped[..., 0][det] < W).all() and
+                              (grouped[..., 1][det] >= 0).all() and (grouped[..., 1][det] < H).all()):
+            raise IndexError("joint coordinates outside the %dx%d heatmap" % (H, W))   # the reference's indexing raises too
         bufs.poses.zero_()
         bufs.poses[0, :P] = torch.from_numpy(np.ascontiguousarray(grouped, dtype=np.float32)).to(hm.device)
         bufs.n_person.fill_(P)

@@ -222,6 +222,10 @@ def decode_op(hm_lo: Sequence[Tensor], hm_hi: Sequence[Tensor], tag: Sequence[Te
               det_thr: float, tag_thr: float, adjust: bool, refine: bool, tag_scale: int) -> List[Tensor]:
     """Network outputs (one list entry per test scale) -> [agg_hm, agg_tags, poses, person_scores, n_person,
     flags, scores_k, idx_k, coords_k, tags_k]."""
+    for name, ts in (("hm_lo", hm_lo), ("hm_hi", hm_hi), ("tag", tag), ("hm_lo_f", hm_lo_f), ("hm_hi_f", hm_hi_f),
+                     ("tag_f", tag_f)):
+        for t in ts:
+            _require_cuda(t, name)
     scales = _scales_from_lists(hm_lo, hm_hi, tag, hm_lo_f, hm_hi_f, tag_f)
     B, K = hm_lo[0].shape[:2]
     E = 2 if len(tag_f) > 0 else 1

@@ -156,7 +156,9 @@ def test_from_preds_and_fallback_dtype(oracle):
                                   "crowd512_30_flip", "netlike512_flip", "crowd256_m5", "crowd256_m32",
                                   "crowd256_tight_thr", "netlike256_some_negative", "crowd192_q_dense"])
 def test_decode_matches_committed_reference_goldens(name):
-    """The CUDA path against tests/golden/*.npz -- outputs of the UNMODIFIED reference, no oracle in between."""
+    """The CUDA path against tests/golden/*.npz -- outputs of the reference's own grouping.py (unmodified) with
+    the restated munkres stand-in underneath it (oracle/refshim/munkres.py, PARITY UNPINNED for equal-cost
+    tie-breaks), recorded by oracle/gen_golden.py; the C++ oracle is not involved."""
     from hpdecode import BottomUpDecoder
     from oracle import golden_cases
     g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", name + ".npz"))

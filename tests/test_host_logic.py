@@ -78,6 +78,38 @@ def test_gather_packed_world2_gloo():
     assert np.array_equal(got, np.arange(15, dtype=np.float32).reshape(5, 3))
 
 
+def _worker_equal(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hpdecode.parallel import gather_packed_equal
+    rows = torch.arange(3 * 4, dtype=torch.float32).reshape(3, 4) + 100 * rank
+    out = torch.full((world * 3, 4), -1.0) if rank == 0 else None
+    got = gather_packed_equal(rows, out, dst=0)
+    if rank == 0:
+        assert got is out
+        q.put(out.numpy())
+    else:
+        assert got is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_packed_equal_world2_gloo():
+    """The equal-shard gather bench.py uses at N > 1: rank r's rows land at [r*b, (r+1)*b) of the preallocated tensor."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_equal, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    base = np.arange(12, dtype=np.float32).reshape(3, 4)
+    assert np.array_equal(got, np.concatenate([base, base + 100]))
+
+
 def test_back_projection_and_coco_records():
     """results.py:158-201 + eval.py:31-47 on the host: identity-like transform keeps coordinates, records
     have the COCO layout."""
