@@ -2,14 +2,20 @@
 """Benchmark of the bottom-up decode path (BASELINE.json: decoded images/s, 512x512, HigherHRNet-W32, flip).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+                    [--workload cfg2|cfg1|cfg3|cfg4] [--scaling weak|strong]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-A step = one pass of the whole decode path (fused aggregation+NMS -> top-k -> grouping -> adjust/refine)
-over one batch of synthetic network outputs; at N > 1 every rank decodes its own batch (images shard
-naturally, weak scaling) and the packed pose lists are gathered on rank 0 with NCCL inside the step.
-Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every field.
+A step = one pass of the whole decode path (fused aggregation+NMS -> top-k -> grouping -> adjust/refine with the
+result-record epilogue) over one batch of synthetic network outputs.  At N > 1 images shard by rank with no
+collective on the hot path; the result records are gathered on rank 0 with NCCL on a separate stream, one
+collective per group of steps.  Rank 0 prints ONE JSON line.  See DESIGN.md "Measurement" for every field.
+
+Workloads (BASELINE.json configs): cfg2 (default) W32 512x512 flip batch 64; cfg1 the same at batch 1;
+cfg3 W48 640x640 test scales 0.5/1.0/1.5 + flip batch 32; cfg4 planted 30-person crowds 512x512 batch 64.
+--scaling weak: every rank decodes its own batch per step; strong: ONE batch split [r*B/N, (r+1)*B/N) (cfg2 as written).
 """
 import argparse
+import hashlib
 import json
 import os
 import statistics
@@ -27,12 +33,35 @@ import numpy as np  # noqa: E402
 K_JOINTS, MAX_PEOPLE, DET_THR, TAG_THR = 17, 30, 0.05, 0.5
 METRIC = "decoded images/s (512x512, HigherHRNet-W32, flip)"
 
+WORKLOADS = {
+    # name: arch (HRNet width), size, batch, test scales, inputs, batches in flight
+    "cfg2": dict(arch=32, size=512, batch=64, scales=(1.0,), inputs="hrnet", streams=8, metric=METRIC,
+                 text="HigherHRNet-W32 {size}x{size}, batch {batch} per GPU, flip test, single scale (BASELINE configs[2], sharded by image)"),
+    "cfg1": dict(arch=32, size=512, batch=1, scales=(1.0,), inputs="hrnet", streams=1,
+                 metric="decoded images/s (512x512, HigherHRNet-W32, flip, batch 1)",
+                 text="HigherHRNet-W32 {size}x{size}, batch {batch}, flip test, single scale, one batch in flight (BASELINE configs[1])"),
+    "cfg3": dict(arch=48, size=640, batch=32, scales=(0.5, 1.0, 1.5), inputs="hrnet", streams=4,
+                 metric="decoded images/s (640x640, HigherHRNet-W48, test scales 0.5/1.0/1.5 + flip)",
+                 text="HigherHRNet-W48 {size}x{size}, test scales 0.5/1.0/1.5 + flip, batch {batch} per GPU, scale-aggregated decode (BASELINE configs[3])"),
+    "cfg4": dict(arch=32, size=512, batch=64, scales=(1.0,), inputs="crowd", streams=8,
+                 metric="decoded images/s (512x512, planted 30-person crowds, flip)",
+                 text="crowded-scene stress: planted 30-person maps {size}x{size}, batch {batch} per GPU, top-k 30, max 30 people (BASELINE configs[4])"),
+}
 
-def algorithmic_bytes_per_image(size: int, flip: bool) -> int:
-    """reads 4*K*f*(q^2+h^2) + 4*K*f*q^2, writes 4*K*S^2*(1+E)."""
+
+def scale_input_size(size: int, s: float) -> int:
+    return int(round(size * s / 64.0)) * 64
+
+
+def algorithmic_bytes_per_image(size: int, scales=(1.0,), flip: bool = True) -> int:
+    """reads 4*K*f*sum_s(q_s^2+h_s^2) + 4*K*f*q_1^2 (tags, scale 1 only), writes 4*K*S^2*(1+E)."""
     f = 2 if flip else 1
-    q, h = size // 4, size // 2
-    return 4 * K_JOINTS * f * (q * q + h * h) + 4 * K_JOINTS * f * q * q + 4 * K_JOINTS * size * size * (1 + f)
+    read = 0
+    for s in scales:
+        n = scale_input_size(size, s)
+        read += 4 * K_JOINTS * f * ((n // 4) ** 2 + (n // 2) ** 2)
+    read += 4 * K_JOINTS * f * (size // 4) ** 2
+    return read + 4 * K_JOINTS * size * size * (1 + f)
 
 
 def make_inputs(batch: int, size: int, seed: int, unique: int = 8, kind: str = "netlike"):
@@ -47,6 +76,30 @@ def make_inputs(batch: int, size: int, seed: int, unique: int = 8, kind: str = "
     return {k: np.ascontiguousarray(np.concatenate([v] * reps)[:batch]) for k, v in base.items()}
 
 
+def resolve(args):
+    wl = dict(WORKLOADS[args.workload])
+    for key in ("batch", "size", "inputs", "streams"):
+        if getattr(args, key) is not None:
+            wl[key] = getattr(args, key)
+    wl["name"] = args.workload
+    wl["tag_scale"] = wl["scales"].index(1.0)
+    return wl
+
+
+def workload_config(wl, args, per_gpu_batch=None):
+    B = wl["batch"] if per_gpu_batch is None else per_gpu_batch
+    per_img = algorithmic_bytes_per_image(wl["size"], wl["scales"])
+    out_mb = B * 4 * K_JOINTS * wl["size"] ** 2 * 3 / 1e6
+    in_mb = B * per_img / 1e6 - out_mb
+    l2 = ("inputs (%.0f MB/batch) and outputs (%.0f MB/batch) exceed the 126 MB L2; no flush needed" % (in_mb, out_mb)
+          if in_mb + out_mb > 4 * 126 else
+          "working set %.0f MB/batch is comparable to the 126 MB L2 and is NOT flushed between steps: batches in flight "
+          "cycle through %d buffer sets; use the default batch for roofline numbers" % (in_mb + out_mb, wl["streams"]))
+    return {"workload": wl["text"].format(size=wl["size"], batch=wl["batch"]), "name": wl["name"],
+            "batch_per_gpu": B, "size": wl["size"], "test_scales": list(wl["scales"]), "flip": True,
+            "max_people": MAX_PEOPLE, "inputs": wl["inputs"], "scaling_mode": args.scaling, "l2": l2}
+
+
 # ------------------------------------------------------------------------------------------------
 # CPU side: the reference arm / cpu_baseline (oracle/py_port.py = the reference's torch-CPU + NumPy calls)
 # ------------------------------------------------------------------------------------------------
@@ -54,8 +107,8 @@ def _cpu_worker(args):
     import torch
     torch.set_num_threads(1)
     from oracle import py_port
-    img, size = args
-    gj, ps = py_port.decode_image([img], (size, size), MAX_PEOPLE, DET_THR, TAG_THR)
+    img_scales, size, tag_scale = args
+    gj, ps = py_port.decode_image(img_scales, (size, size), MAX_PEOPLE, DET_THR, TAG_THR, tag_scale)
     return gj.shape[0]
 
 
@@ -63,16 +116,18 @@ class CpuPool:
     """One process per host core, each decoding whole images with the Python port (how the reference runs:
     one image per call, single-threaded NumPy/Python; the pool is the fair multi-core figure)."""
 
-    def __init__(self, size: int, cores: int, inputs):
+    def __init__(self, size: int, cores: int, host_scales, tag_scale: int):
         import multiprocessing as mp
-        self.size, self.cores = size, cores
-        self.images = [{k: v[i] for k, v in inputs.items()} for i in range(inputs["hm_lo"].shape[0])]
+        self.size, self.cores, self.tag_scale = size, cores, tag_scale
+        n = host_scales[0]["hm_lo"].shape[0]
+        self.images = [[{k: v[i] for k, v in s.items()} for s in host_scales] for i in range(n)]
         self.pool = mp.get_context("spawn").Pool(cores)
-        self.pool.map(_cpu_worker, [(self.images[0], size)] * cores)     # import torch + warm caches, untimed
+        self.pool.map(_cpu_worker, [(self.images[0], size, tag_scale)] * cores)     # import torch + warm caches, untimed
 
     def step(self, n_images: int) -> float:
         t = time.perf_counter()
-        self.pool.map(_cpu_worker, [(self.images[i % len(self.images)], self.size) for i in range(n_images)], chunksize=1)
+        self.pool.map(_cpu_worker, [(self.images[i % len(self.images)], self.size, self.tag_scale) for i in range(n_images)],
+                      chunksize=1)
         return time.perf_counter() - t
 
     def close(self):
@@ -87,21 +142,32 @@ def host_cores() -> int:
         return os.cpu_count() or 1
 
 
+def produce_inputs(wl, batch, seed, dev):
+    """One dict of tensors per test scale, on ``dev`` (GPU for the hrnet inputs when there is one)."""
+    import torch
+    if wl["inputs"] == "hrnet":
+        # BASELINE: heatmaps / tags "produced by random-init HigherHRNet weights on synthetic images"
+        from hpdecode import synth_net
+        return [synth_net.network_outputs(batch, scale_input_size(wl["size"], s), flip=True, seed=seed, C=wl["arch"],
+                                          device=dev, chunk=8 if wl["size"] <= 512 else 4) for s in wl["scales"]]
+    if len(wl["scales"]) != 1:
+        raise SystemExit("--inputs netlike|crowd are single-scale generators")
+    host = make_inputs(batch, wl["size"], seed=seed, kind=wl["inputs"])
+    return [{k: torch.from_numpy(v).to(dev) for k, v in host.items()}]
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    import torch
+    wl = resolve(args)
     cores = min(host_cores(), 32)
-    if args.inputs == "hrnet":
-        import torch
-        from hpdecode import synth_net
-        dev = "cuda:0" if torch.cuda.is_available() else "cpu"      # producing the inputs is not part of the timed path
-        r = synth_net.network_outputs(min(8, args.batch), args.size, flip=True, seed=1, C=32, device=dev, chunk=2)
-        inputs = {k: v.contiguous().cpu().numpy() for k, v in r.items()}
-    else:
-        inputs = make_inputs(min(8, args.batch), args.size, seed=1, kind=args.inputs)
-    pool = CpuPool(args.size, cores, inputs)
-    sample = cores                                     # one image per core per step (~6 s of wall clock)
+    dev = "cuda:0" if torch.cuda.is_available() else "cpu"      # producing the inputs is not part of the timed path
+    ins = produce_inputs(wl, min(8, wl["batch"]), 1, dev)
+    host_scales = [{k: v.contiguous().cpu().numpy() for k, v in s.items()} for s in ins]
+    pool = CpuPool(wl["size"], cores, host_scales, wl["tag_scale"])
+    sample = cores                                     # one image per core per step (~6 s of wall clock at 512x512)
     for _ in range(args.warmup):
         pool.step(sample)
     times = [pool.step(sample) for _ in range(args.steps)]
@@ -109,29 +175,16 @@ def run_reference(args):
     total = sum(times)
     value = sample * args.steps / total
     line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "images/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": wl["metric"], "value": value, "unit": "images/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / args.steps,
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": workload_config(args),
+        "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(wl, args),
         "cpu_baseline": {"value": value, "unit": "images/s", "cores": cores, "kind": "port",
                          "sample": f"{sample} images per step (one per core), oracle/py_port.py = the reference's "
                                    "torch-CPU/NumPy/munkres calls; the reference itself is Python and cannot travel"},
         "e2e": {"value": value, "unit": "images/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
-
-
-def workload_config(args):
-    in_mb = args.batch * (algorithmic_bytes_per_image(args.size, True) - 4 * K_JOINTS * args.size * args.size * 3) / 1e6
-    out_mb = args.batch * 4 * K_JOINTS * args.size * args.size * 3 / 1e6
-    l2 = ("inputs (%.0f MB/batch) and outputs (%.0f MB/batch) exceed the 126 MB L2; no flush needed" % (in_mb, out_mb)
-          if in_mb + out_mb > 4 * 126 else
-          "working set %.0f MB/batch is comparable to the 126 MB L2 and is NOT flushed between steps: use the default "
-          "batch for roofline numbers" % (in_mb + out_mb))
-    return {"workload": f"HigherHRNet-W32 {args.size}x{args.size}, batch {args.batch} per GPU, flip test, single scale "
-                        "(BASELINE configs[2], sharded by image)",
-            "batch_per_gpu": args.batch, "size": args.size, "flip": True, "max_people": MAX_PEOPLE, "inputs": args.inputs,
-            "l2": l2}
 
 
 # ------------------------------------------------------------------------------------------------
@@ -208,11 +261,31 @@ def measured_peak():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def bind_to_gpu_numa_node(index: int):
+    """Pin this process to the CPUs NVML reports as local to the GPU while the pinned staging buffers are allocated
+    (first-touch then places the pages on the GPU's NUMA node).  Returns (note for the JSON line, affinity to restore)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (os.cpu_count() + 63) // 64)
+        cpus = {64 * i + b for i, w in enumerate(words) for b in range(64) if (w >> b) & 1}
+        allowed = os.sched_getaffinity(0)
+        local = cpus & allowed
+        if local and local != allowed:
+            os.sched_setaffinity(0, local)
+            return "allocated while bound to the %d GPU-local CPUs of %d" % (len(local), len(allowed)), allowed
+        return "GPU lists all %d allowed CPUs as local (one NUMA node): nothing to bind" % len(allowed), None
+    except Exception as e:      # noqa: BLE001
+        return "no NVML affinity (%s)" % type(e).__name__, None
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
-    from hpdecode import BottomUpDecoder, ops
-    from hpdecode.parallel import gather_packed_equal
+    from hpdecode import BottomUpDecoder, DecodePipeline, ops
+    from hpdecode.decoder import DecodeResult
+    from hpdecode.parallel import gather_rows, shard_range
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -222,44 +295,91 @@ def run_ours(args):
             raise SystemExit("launch N > 1 with: python -m torch.distributed.run --nproc-per-node N bench.py --gpus N")
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    numa_note, old_affinity = bind_to_gpu_numa_node(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     sampler = ClockSampler(local) if rank == 0 else None     # attaches while the inputs are produced
 
-    B, S = args.batch, args.size
-    if args.inputs == "hrnet":
-        # BASELINE: heatmaps / tags "produced by random-init HigherHRNet weights on synthetic images"
-        from hpdecode import synth_net
-        resident = synth_net.network_outputs(B, S, flip=True, seed=1 + rank, C=32, device=dev)
-        torch.cuda.synchronize()
-        pinned = {k: v.contiguous().cpu().pin_memory() for k, v in resident.items()}
-        host = {k: v[: min(8, B)].numpy() for k, v in pinned.items()}
+    wl = resolve(args)
+    S, scales_cfg, tag_scale = wl["size"], wl["scales"], wl["tag_scale"]
+    if args.scaling == "strong":
+        # cfg2 as written: ONE batch, images [r*B/N, (r+1)*B/N) on rank r.  Every rank builds the same batch
+        # (same seed) and keeps its shard, so N ranks together decode exactly the N = 1 batch.
+        total_batch = wl["batch"]
+        b0, b1 = shard_range(total_batch, rank, world)
+        if b1 - b0 < 1 or total_batch % world:
+            raise SystemExit("--scaling strong needs the batch to be a multiple of the number of GPUs")
+        full = produce_inputs(wl, total_batch, 1, dev)
+        resident = [{k: v[b0:b1] for k, v in s.items()} for s in full]
+        B = b1 - b0
     else:
-        host = make_inputs(B, S, seed=1 + rank, kind=args.inputs)
-        pinned = {k: torch.from_numpy(v).pin_memory() for k, v in host.items()}
-        resident = {k: v.to(dev) for k, v in pinned.items()}
+        B = wl["batch"]
+        total_batch = B * world
+        resident = produce_inputs(wl, B, 1 + rank, dev)
+    torch.cuda.synchronize()
+    pinned = [{k: v.contiguous().cpu().pin_memory() for k, v in s.items()} for s in resident]
+    host = [{k: v[: min(8, B)].numpy() for k, v in s.items()} for s in pinned]
+    E = 2
     dec = BottomUpDecoder(K_JOINTS, MAX_PEOPLE, DET_THR, TAG_THR, dev)
-    params = ops.make_params(B, K_JOINTS, S, S, 2, MAX_PEOPLE, DET_THR, TAG_THR)
-    F = MAX_PEOPLE * K_JOINTS * 5 + MAX_PEOPLE + 2
-    from hpdecode.decoder import DecodeResult
+    params = ops.make_params(B, K_JOINTS, S, S, E, MAX_PEOPLE, DET_THR, TAG_THR, num_scales=len(scales_cfg), tag_scale=tag_scale)
+    ROW = ops.record_layout(K_JOINTS, MAX_PEOPLE, E).row_bytes
 
     # DecodePipeline keeps NS batches in flight: batch i+1's bandwidth-bound aggregation kernel overlaps batch
-    # i's latency-bound top-k / grouping / refine kernels (high-priority streams, a few SMs each).
-    from hpdecode.decoder import DecodePipeline
-    NS = max(1, args.streams)
-    pipe = DecodePipeline(dec, depth=NS, split_priority=args.split_priority)
-    extra = [{"gathered": torch.empty((world * B, F), device=dev) if (world > 1 and rank == 0) else None,
-              "staging": {k: torch.empty(v.shape, device=dev, dtype=v.dtype) for k, v in resident.items()},
-              "result_host": torch.empty((B, F), dtype=torch.float32).pin_memory()} for _ in range(NS)]
-    stages = ("aggregate_nms", "topk", "group", "adjust_refine")
+    # i's latency-bound top-k / grouping / refine kernels.  Lane i's records land in ring[i]; every G lanes the block
+    # ring[g*G:(g+1)*G] is gathered on rank 0 by ONE collective on a separate stream (and, in the e2e region, copied to
+    # pinned host memory), so no decode stream ever waits for a peer.
+    NS = max(1, wl["streams"])
+    G = max(1, NS // 2) if args.gather_every is None else max(1, min(args.gather_every, NS))
+    while NS % G:
+        G -= 1
+    n_groups = NS // G
+    ring = torch.empty((NS, B, ROW), device=dev, dtype=torch.uint8)
+    use_graphs = args.graphs == "on" or (args.graphs == "auto" and B < 32)
+    pipe = DecodePipeline(dec, depth=NS, records_ring=ring, use_graphs=use_graphs)
+    comm = torch.cuda.Stream(device=dev)
+    gathered = [torch.empty((world, G * B * ROW), device=dev, dtype=torch.uint8) if (world > 1 and rank == 0) else None
+                for _ in range(n_groups)]
+    result_host = [torch.empty((world, G * B * ROW), dtype=torch.uint8).pin_memory() if rank == 0 else None
+                   for _ in range(n_groups)]
+    staging = [[{k: torch.empty(v.shape, device=dev, dtype=v.dtype) for k, v in s.items()} for s in resident] for _ in range(NS)]
+    if old_affinity is not None:
+        os.sched_setaffinity(0, old_affinity)
+    group_done = [torch.cuda.Event() for _ in range(n_groups)]
+    lane_done = [torch.cuda.Event() for _ in range(NS)]
+    state = {"to_host": False, "pending": []}
     main = torch.cuda.current_stream(dev)
-    bufs = dec.buffers(B, S, S, 2, slot=0)
+    bufs = dec.buffers(B, S, S, E, slot=NS)            # a buffer set of its own for the sequential stage timing
 
-    def finish(ln, res):
-        packed = res.packed()
-        if world > 1:
-            gather_packed_equal(packed, extra[ln["slot"]]["gathered"], dst=0)
-        return packed
+    def flush_group(lanes):
+        """Gather (and optionally copy to the host) the records of these consecutive lanes on the comm stream."""
+        if not lanes:
+            return
+        g = lanes[0] // G
+        for i in lanes:
+            comm.wait_event(lane_done[i])
+        with torch.cuda.stream(comm):
+            block = ring[lanes[0]: lanes[0] + len(lanes)].view(-1)
+            src = block
+            if world > 1:
+                out = gathered[g][:, : block.numel()] if rank == 0 else None
+                if len(lanes) != G and rank == 0:
+                    out = torch.empty((world, block.numel()), device=dev, dtype=torch.uint8)
+                gather_rows(block, out, dst=0)
+                src = out
+            if state["to_host"] and rank == 0:
+                dst = result_host[g][: (world if world > 1 else 1), : block.numel()]
+                dst.copy_(src.view(dst.shape), non_blocking=True)
+            group_done[g].record(comm)
+        for i in lanes:
+            pipe.lanes[i]["gate"] = group_done[g]       # the lane's records may be overwritten only after this
+
+    def after_tail(ln, res):
+        i = ln["slot"]
+        lane_done[i].record()
+        state["pending"].append(i)
+        if len(state["pending"]) == G or i == NS - 1:
+            flush_group(state["pending"])
+            state["pending"] = []
 
     def barrier():
         if world > 1:
@@ -267,34 +387,35 @@ def run_ours(args):
         torch.cuda.synchronize()
 
     def run_steps(n, submit):
-        """n pipelined steps; returns device time (ms) from fork to join on the main stream."""
+        """n pipelined steps; returns device time (ms) from fork to join (decode lanes + gathers) on the main stream."""
         t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         barrier()
+        pipe._next = 0
         t0.record(main)
         for _ in range(n):
             submit()
+        flush_group(state["pending"])
+        state["pending"] = []
         pipe.drain()
         t1.record(main)
         barrier()
         return t0.elapsed_time(t1)
 
     def value_step():
-        pipe.submit([resident], (S, S), after_tail=finish)
+        pipe.submit(resident, (S, S), tag_scale=tag_scale, after_tail=after_tail)
 
     def parity_check():
         """Before anything is timed: decode this rank's batch once and compare images of it with the CPU oracle
         (bit-exact grouped joints and person scores); at N > 1 rank 0 also compares every rank's gathered rows
         with a checksum the owning rank computed locally."""
-        import hashlib
         from oracle import cpu_oracle      # the checker, never the thing measured
-        res = dec.decode([resident], (S, S), slot=NS)
-        packed = res.packed()
-        rows = packed.cpu().numpy()
-        out = DecodeResult.unpack(rows, MAX_PEOPLE, K_JOINTS, 2)
-        n_check = min(max(1, 8 // world), len(host["hm_lo"]), B)
+        res = dec.decode(resident, (S, S), tag_scale=tag_scale, slot=NS + 1)
+        rows = res.records.cpu().numpy()
+        out = DecodeResult.unpack(rows, MAX_PEOPLE, K_JOINTS, E)
+        n_check = min(max(1, 8 // world), len(host[0]["hm_lo"]), B)
         ok = True
         for b in range(n_check):
-            hm_o, tg_o = cpu_oracle.aggregate([{k: v[b] for k, v in host.items()}], (S, S))
+            hm_o, tg_o = cpu_oracle.aggregate([{k: v[b] for k, v in s.items()} for s in host], (S, S), tag_scale=tag_scale)
             ref = cpu_oracle.parse(hm_o, tg_o, MAX_PEOPLE, DET_THR, TAG_THR)
             gj, ps = out[b]
             ok = ok and gj.shape == ref["grouped_joints"].shape and \
@@ -307,34 +428,37 @@ def run_ours(args):
             dist.all_gather(digests, digest)
             flag = torch.tensor([int(ok)], device=dev)
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
-            gathered = torch.empty((world * B, F), device=dev) if rank == 0 else None
-            gather_packed_equal(packed, gathered, dst=0)
+            out_rows = torch.empty((world, B * ROW), device=dev, dtype=torch.uint8) if rank == 0 else None
+            gather_rows(res.records.view(-1), out_rows, dst=0)
             info["ok"] = bool(flag.item())
             if rank == 0:
-                g = gathered.cpu().numpy()
-                same = [hashlib.sha256(g[r * B:(r + 1) * B].tobytes()).digest() == bytes(digests[r].cpu().tolist())
-                        for r in range(world)]
+                g = out_rows.cpu().numpy()
+                same = [hashlib.sha256(g[r].tobytes()).digest() == bytes(digests[r].cpu().tolist()) for r in range(world)]
                 info["gathered_rows_match_rank_checksums"] = bool(all(same))
                 info["ok"] = info["ok"] and all(same)
         return info
 
     parity = parity_check()
     if rank == 0 and not parity["ok"]:
-        print(json.dumps({"metric": METRIC, "error": "parity check against the oracle FAILED; nothing was timed", "parity": parity}),
-              flush=True)
+        print(json.dumps({"metric": wl["metric"], "error": "parity check against the oracle FAILED; nothing was timed",
+                          "parity": parity}), flush=True)
     if not parity["ok"]:
         raise SystemExit(3)
 
     # ---- value: inputs resident in HBM -------------------------------------------------------------
-    run_steps(max(args.warmup, 3) * NS, value_step)
+    W = max(args.warmup, 3)
+    run_steps(W * NS, value_step)
     if sampler:
         sampler.mark_start()
     # per-stage durations: K sequential steps, one batch in flight, CUDA events on the launching stream
+    stages = DecodePipeline.STAGES
     evs = [[torch.cuda.Event(enable_timing=True) for _ in range(len(stages) + 1)] for _ in range(args.steps)]
+    for st in stages:
+        ops.run_stage(st, bufs, params, scales=resident)
     for i in range(args.steps):
         for j, st in enumerate(stages):
             evs[i][j].record()
-            ops.run_stage(st, bufs, params, scales=[resident])
+            ops.run_stage(st, bufs, params, scales=resident)
         evs[i][len(stages)].record()
     barrier()
     stage_ms = [statistics.mean(evs[i][j].elapsed_time(evs[i][j + 1]) for i in range(args.steps)) for j in range(len(stages))]
@@ -343,25 +467,27 @@ def run_ours(args):
     ms_total = run_steps(args.steps, value_step)
     launches = ops.launches_total() - l0
 
-    # ---- e2e: host buffers, H2D of the inputs and D2H of the pose lists inside the timed region ---------
+    # ---- e2e: host buffers, H2D of the inputs and D2H of the result records inside the timed region ---------
+    state["to_host"] = True
+
     def e2e_step():
         def h2d(ln):
-            st = extra[ln["slot"]]["staging"]
-            for k in st:
-                st[k].copy_(pinned[k], non_blocking=True)
-            return [st]
+            st = staging[ln["slot"]]
+            for s_dst, s_src in zip(st, pinned):
+                for k in s_dst:
+                    s_dst[k].copy_(s_src[k], non_blocking=True)
+            return st
 
-        def d2h(ln, res):
-            packed = finish(ln, res)
-            src = extra[ln["slot"]]["gathered"] if (world > 1 and rank == 0) else packed
-            extra[ln["slot"]]["result_host"].copy_(src[:B], non_blocking=True)
-
-        pipe.submit([resident], (S, S), before_agg=h2d, after_tail=d2h)
+        pipe.submit(resident, (S, S), tag_scale=tag_scale, before_agg=h2d, after_tail=after_tail)
 
     run_steps(2 * NS, e2e_step)
     e2e_steps = max(3, min(args.steps, 10))
     e2e_ms = run_steps(e2e_steps, e2e_step)
     clocks = sampler.stop() if sampler else None
+    e2e_ok = None
+    if rank == 0:   # the host copy of the last full group really holds every rank's records
+        last = host_records_sane(result_host[0], world, G, B, ROW)
+        e2e_ok = last
 
     # max over ranks
     if world > 1:
@@ -372,43 +498,48 @@ def run_ours(args):
     if rank == 0:
         n_person = bufs.n_person.cpu().numpy()
         peak, peak_src = measured_peak()
-        bytes_launch = B * algorithmic_bytes_per_image(S, True)
+        bytes_launch = B * algorithmic_bytes_per_image(S, scales_cfg)
         achieved = bytes_launch / (stage_ms[0] * 1e-3) / 1e9
         traffic = None
         tp = os.path.join(ROOT, "profiles", "roofline_traffic.json")
-        if os.path.isfile(tp):
+        if os.path.isfile(tp) and wl["name"] in ("cfg2", "cfg3") and B == WORKLOADS[wl["name"]]["batch"]:
             try:
-                traffic = json.load(open(tp)).get("agg_nms_dram_bytes_per_launch")
+                tj = json.load(open(tp))
+                traffic = tj.get("agg_nms_dram_bytes_per_launch" if wl["name"] == "cfg2" else "agg_nms_ms_dram_bytes_per_launch")
             except Exception:
                 traffic = None
+        imgs_per_step = total_batch
         line = {
-            "metric": METRIC, "value": world * B * args.steps / (ms_total * 1e-3), "unit": "images/s",
-            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
-            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-            "data": ("synthetic: outputs of a default-init HigherHRNet-W32 (stock PyTorch, hpdecode/synth_net.py) on seeded N(0,1) "
-                     "images, flipped forward included; no dataset/checkpoint offline") if args.inputs == "hrnet" else
-                    "synthetic (seeded smooth random fields with default-init HigherHRNet value ranges)",
-            "config": workload_config(args),
+            "metric": wl["metric"], "value": imgs_per_step * args.steps / (ms_total * 1e-3), "unit": "images/s",
+            "n_gpus": world, "steps": args.steps, "warmup": W, "ms_per_step": ms_total / args.steps,
+            "higher_is_better": True, "scaling": args.scaling, "vs_baseline": None, "dtype": "f32",
+            "data": ("synthetic: outputs of a default-init HigherHRNet-W%d (stock PyTorch, hpdecode/synth_net.py) on seeded N(0,1) "
+                     "images, flipped forward included; no dataset/checkpoint offline" % wl["arch"]) if wl["inputs"] == "hrnet" else
+                    "synthetic (%s)" % ("planted 30-person Gaussian peaks with per-person tags, SURVEY 8(d)-5" if wl["inputs"] == "crowd"
+                                        else "seeded smooth random fields with default-init HigherHRNet value ranges"),
+            "config": workload_config(wl, args, B),
             "roofline": {"bound": "hbm", "kernel": "agg_nms (fused aggregation + NMS)", "achieved": achieved, "peak": peak,
                          "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": bytes_launch, "kernel_ms": stage_ms[0],
                          "timing": "CUDA events around each of the K launches, one batch in flight"},
             "stage_ms": dict(zip(stages, stage_ms)), "sequential_ms_per_step": seq_ms, "streams": NS,
+            "cuda_graphs": bool(use_graphs), "gather": {"steps_per_collective": G, "stream": "dedicated", "row_bytes": ROW},
             "grouping": {"kernel_ms": stage_ms[2], "latency_us_per_image": 1e3 * stage_ms[2],
                          "amortised_us_per_image": 1e3 * stage_ms[2] / B, "resident_warps": 4 * B,
                          "sm_occupancy_pct": 100.0 * 4 * B / (torch.cuda.get_device_properties(dev).multi_processor_count * 64),
                          "note": "one CTA of four warps per image; all images of a batch run concurrently, so the kernel duration is "
                                  "each image's latency"},
             "persons_per_image": float(n_person.mean()),
-            "e2e": {"value": world * B * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
-                    "h2d_bytes_per_step": int(sum(v.numel() * 4 for v in pinned.values())) * world,
-                    "d2h_bytes_per_step": int(B * F * 4), "steps": e2e_steps},
+            "e2e": {"value": imgs_per_step * e2e_steps / (e2e_ms * 1e-3), "unit": "images/s",
+                    "h2d_bytes_per_step": int(sum(v.numel() * v.element_size() for s in pinned for v in s.values())) * world,
+                    "d2h_bytes_per_step": int(world * B * ROW), "steps": e2e_steps,
+                    "host_copy_holds_every_rank": e2e_ok, "pinned_staging": numa_note},
             "gpu_launches": launches, "clocks": clocks, "parity": parity,
         }
         if world == 1 and not args.no_cpu_baseline:
             cores = min(host_cores(), 32)
-            pool = CpuPool(S, cores, {k: v[:8] for k, v in host.items()})
-            sample = cores * 2
+            pool = CpuPool(S, cores, host, tag_scale)
+            sample = cores * 2 if S <= 512 and len(scales_cfg) == 1 else cores
             sec = pool.step(sample)
             pool.close()
             line["cpu_baseline"] = {"value": sample / sec, "unit": "images/s", "cores": cores, "kind": "port",
@@ -419,19 +550,33 @@ def run_ours(args):
         dist.destroy_process_group()
 
 
+def host_records_sane(host_block, world, G, B, ROW) -> bool:
+    """Every rank's slice of the host copy parses as records with a sane person count (the D2H really carried
+    world * G * B rows, not just rank 0's)."""
+    from hpdecode.decoder import Records
+    n = world if world > 1 else 1
+    raw = host_block[:n].numpy().reshape(n * G * B, ROW)
+    rec = Records(raw, MAX_PEOPLE, K_JOINTS, 2)
+    return bool(((rec.n_person >= 1) & (rec.n_person <= MAX_PEOPLE)).all())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--batch", type=int, default=64)
-    ap.add_argument("--size", type=int, default=512)
+    ap.add_argument("--workload", default="cfg2", choices=sorted(WORKLOADS))
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"])
+    ap.add_argument("--batch", type=int, default=None)
+    ap.add_argument("--size", type=int, default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--split-priority", action="store_true")
-    ap.add_argument("--inputs", default="hrnet", choices=["hrnet", "netlike", "crowd"],
-                    help="hrnet: outputs of a default-init HigherHRNet-W32 on seeded random images; netlike: CPU-generated fields")
-    ap.add_argument("--streams", type=int, default=8, help="batches in flight per GPU (1 = strictly sequential)")
+    ap.add_argument("--inputs", default=None, choices=["hrnet", "netlike", "crowd"],
+                    help="hrnet: outputs of a default-init HigherHRNet on seeded random images; netlike / crowd: CPU-generated fields")
+    ap.add_argument("--streams", type=int, default=None, help="batches in flight per GPU (1 = strictly sequential)")
+    ap.add_argument("--gather-every", type=int, default=None, help="steps per gather collective (default: streams / 2)")
+    ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
+                    help="CUDA graphs for the per-step launches (auto: per-GPU batch < 32)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

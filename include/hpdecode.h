@@ -33,7 +33,7 @@ extern "C" {
 #define HPD_EXPORT
 #endif
 
-#define HPD_ABI_VERSION 1
+#define HPD_ABI_VERSION 2
 #define HPD_MAX_KPTS 32     /* joints per person (COCO: 17) */
 #define HPD_MAX_PEOPLE 32   /* max_num_people == top-k; the warp-wide Hungarian handles n <= 32 */
 #define HPD_MAX_EMB 2       /* tag embedding dims: 1 (no flip test) or 2 (flip test) */
@@ -46,12 +46,20 @@ enum {
   HPD_ECUDA = 3         /* a CUDA call failed (launch configuration, etc.) */
 };
 
-/* One float32 NCHW tensor view. */
+enum {
+  HPD_F32 = 0,          /* float32 maps (inference path, model.py:78-111) */
+  HPD_F16 = 1           /* IEEE half maps: the validation-time caller runs the net under autocast
+                         * (module.py:78,100-110); values are widened on load, all arithmetic stays float32 */
+};
+
+/* One NCHW tensor view. */
 typedef struct HpdMap {
-  const float* ptr;   /* NULL = absent */
+  const void* ptr;    /* NULL = absent */
   int64_t stride_b;   /* elements between images */
   int64_t stride_c;   /* elements between channels; rows are contiguous (stride_y == w) */
   int32_t h, w;
+  int32_t dtype;      /* HPD_F32 or HPD_F16; all maps of one call share it */
+  int32_t reserved_;
 } HpdMap;
 
 /* Raw network outputs for one test scale: the un-flipped forward and, when the flip test is on,
@@ -101,7 +109,39 @@ typedef struct HpdBuffers {
   int32_t* flags;       /* [B]            bit0: empty-scene fallback fired (grouping.py:262-269)  */
   float* tag_bmin;      /* [B,K,HB,WPR]   HB = (H+3)/4: lower / upper bound of the first tag component over     */
   float* tag_bmax;      /* [B,K,HB,WPR]   4 image rows x one 32-pixel word (refine prefilter; -inf/+inf = none) */
+  uint8_t* records;     /* [B][row_bytes] optional (NULL = not written): one result record per image, laid out as
+                         * hpd_record_layout() says; written by the epilogue of hpd_adjust_refine / hpd_decode     */
+  const double* inv_affine; /* [B][6] optional: per-image 2x3 matrix (row major) that maps network-input pixels back
+                         * to the raw image, i.e. get_affine_transform(center, scale, 0, (W, H), inverse=True)
+                         * (results.py:158-171, base/transforms/utils.py:25-57).  NULL = identity              */
 } HpdBuffers;
+
+/* Layout of one result record (all offsets in bytes from the start of the image's row; row_bytes % 8 == 0).
+ * The record is everything the reference's callers read after a decode, ready for ONE device->host copy:
+ *   coco          f64 [M][3K+1]  per person (x, y, 1) * K then the person score: the "keypoints" list and "score"
+ *                                of evaluate_dataset's COCO record (bin/eval.py:31-47) with x, y back-projected to
+ *                                the raw image (results.py:158-171,189-201,244).  Persons >= n_person: zeros.
+ *                                Like the reference, back-projected coordinates are rounded to float32 (they are
+ *                                written into a float32 array, results.py:165-170) -- except in the empty-scene
+ *                                fallback, whose pseudo-person is float64 throughout (grouping.py:262-269).
+ *   poses         f32 [M][K][3+E] grouped joints in network-input pixels (x, y, score, tags), grouping.py:283
+ *   person_scores f32 [M]        grouping.py:276
+ *   n_person      i32            persons returned
+ *   flags         i32            bit 0: empty-scene fallback fired                                              */
+typedef struct HpdRecordLayout {
+  int64_t row_bytes;
+  int64_t off_coco, off_poses, off_person_scores, off_n_person, off_flags;
+  int32_t coco_stride;  /* doubles per person: 3K + 1 */
+  int32_t reserved_;
+} HpdRecordLayout;
+
+/* One raw image for hpd_prepare_input: uint8, HWC, 3 channels, resident on the device. */
+typedef struct HpdImage {
+  const uint8_t* ptr;
+  int64_t stride_row;   /* bytes between rows (>= 3*w) */
+  int32_t h, w;
+  double m[6];          /* the forward 2x3 matrix cv2.warpAffine receives (base/transforms/utils.py:95-96) */
+} HpdImage;
 
 HPD_EXPORT int hpd_abi_version(void);
 HPD_EXPORT const char* hpd_last_error_string(void);
@@ -133,8 +173,9 @@ HPD_EXPORT int hpd_topk(const HpdParams* p, const HpdBuffers* buf, void* stream)
 HPD_EXPORT int hpd_group(const HpdParams* p, const HpdBuffers* buf, void* stream);
 
 /* (e) adjust + person score + refine: grouping.py:172-191, :276, :193-250.
- * Reads agg_hm, agg_tags, hm_wmax, tag_bmin, tag_bmax, idx_k, scores_k, n_person; updates poses in place;
- * writes person_scores. */
+ * Reads agg_hm, agg_tags, hm_wmax, tag_bmin, tag_bmax, idx_k, scores_k, n_person, flags; updates poses in place;
+ * writes person_scores and, if buf->records is given, the per-image result records (back-projection through
+ * buf->inv_affine + COCO layout, results.py:158-201,240-244, bin/eval.py:31-47) in the epilogue of its last kernel. */
 HPD_EXPORT int hpd_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* workspace, size_t workspace_bytes,
                       void* stream);
 
@@ -143,6 +184,28 @@ HPD_EXPORT int hpd_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void
  * (the MPPEHeatmapParser.parse entry, grouping.py:252). */
 HPD_EXPORT int hpd_decode(const HpdParams* p, const HpdScaleInputs* scales, const HpdBuffers* buf, void* workspace,
                size_t workspace_bytes, void* stream);
+
+/* Offsets and size of the per-image result record for these params (num_kpts, max_people, emb). */
+HPD_EXPORT int hpd_record_layout(const HpdParams* p, HpdRecordLayout* out);
+
+/* ---- input side: InferenceKeypointsModel.prepare_input, model.py:70-76 ---------------------
+ * Host-side geometry, float64 like the reference (no device work, no stream):
+ * get_multi_scale_size (base/transforms/utils.py:60-87): resized (w, h), center, scale of an img_h x img_w image. */
+HPD_EXPORT int hpd_multi_scale_size(int img_h, int img_w, int input_size, double current_scale, double min_scale,
+                                    int32_t size_resized_wh[2], int32_t center_xy[2], double scale_wh[2]);
+
+/* get_affine_transform(center, scale, rot=0, output_size, inverse) (base/transforms/utils.py:25-57): float32 point
+ * triples, then cv2.getAffineTransform's 6x6 LU solve replayed in float64 (bit-identical to OpenCV 4.x). */
+HPD_EXPORT int hpd_get_affine_transform(const double center_xy[2], const double scale_wh[2], const int32_t output_size_wh[2],
+                                        int inverse, double m_out[6]);
+
+/* resize_align_multi_scale's cv2.warpAffine (INTER_LINEAR, BORDER_CONSTANT 0; base/transforms/utils.py:96) followed by
+ * T.ToTensor + T.Normalize (model.py:45-50): images_host[b] (uint8 HWC on the device, descriptors on the host) ->
+ * out [batch,3,out_h,out_w] float32.  The warp replays OpenCV's fixed-point arithmetic (10-bit coordinates, 5-bit
+ * sub-pixel positions, 15-bit weights) and the normalisation torch's float32 sequence, so out is bit-identical to
+ * the reference's tensor.  mean / std: 3 floats each (host). */
+HPD_EXPORT int hpd_prepare_input(const HpdImage* images_host, int batch, float* out, int out_h, int out_w,
+                                 const float mean[3], const float std_[3], void* stream);
 
 /* Number of kernel launches the previous call on this thread enqueued (for bench accounting). */
 HPD_EXPORT int hpd_last_launch_count(void);

@@ -433,6 +433,7 @@ int check_map(const HpdMap& m, const char* name, bool required) {
     return HPD_OK;
   }
   if (m.h <= 0 || m.w <= 0) { set_error("%s: bad size %dx%d", name, m.h, m.w); return HPD_EINVAL; }
+  if (m.dtype != HPD_F32) { set_error("%s: unsupported dtype code %d", name, m.dtype); return HPD_EINVAL; }
   return HPD_OK;
 }
 
@@ -466,10 +467,10 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
       return HPD_EINVAL;
     }
     ScaleDev& S = a.sc[s];
-    S.lo = in.hm_lo.ptr; S.lo_sb = in.hm_lo.stride_b; S.lo_sc = in.hm_lo.stride_c;
-    S.hi = in.hm_hi.ptr; S.hi_sb = in.hm_hi.stride_b; S.hi_sc = in.hm_hi.stride_c;
-    S.lo_f = in.hm_lo_f.ptr; S.lof_sb = in.hm_lo_f.stride_b; S.lof_sc = in.hm_lo_f.stride_c;
-    S.hi_f = in.hm_hi_f.ptr; S.hif_sb = in.hm_hi_f.stride_b; S.hif_sc = in.hm_hi_f.stride_c;
+    S.lo = (const float*)in.hm_lo.ptr; S.lo_sb = in.hm_lo.stride_b; S.lo_sc = in.hm_lo.stride_c;
+    S.hi = (const float*)in.hm_hi.ptr; S.hi_sb = in.hm_hi.stride_b; S.hi_sc = in.hm_hi.stride_c;
+    S.lo_f = (const float*)in.hm_lo_f.ptr; S.lof_sb = in.hm_lo_f.stride_b; S.lof_sc = in.hm_lo_f.stride_c;
+    S.hi_f = (const float*)in.hm_hi_f.ptr; S.hif_sb = in.hm_hi_f.stride_b; S.hif_sc = in.hm_hi_f.stride_c;
     S.lh = in.hm_lo.h; S.lw = in.hm_lo.w; S.hh = in.hm_hi.h; S.hw = in.hm_hi.w;
     S.s_lo_y = (float)S.lh / (float)S.hh; S.s_lo_x = (float)S.lw / (float)S.hw;
     S.s_hi_y = (float)S.hh / (float)a.H; S.s_hi_x = (float)S.hw / (float)a.W;
@@ -487,8 +488,8 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
       set_error("emb must be 2 iff the flipped-run tag map is given (got emb=%d)", p->emb);
       return HPD_EINVAL;
     }
-    a.tag = in.tag.ptr; a.tag_sb = in.tag.stride_b; a.tag_sc = in.tag.stride_c;
-    a.tag_f = in.tag_f.ptr; a.tagf_sb = in.tag_f.stride_b; a.tagf_sc = in.tag_f.stride_c;
+    a.tag = (const float*)in.tag.ptr; a.tag_sb = in.tag.stride_b; a.tag_sc = in.tag.stride_c;
+    a.tag_f = (const float*)in.tag_f.ptr; a.tagf_sb = in.tag_f.stride_b; a.tagf_sc = in.tag_f.stride_c;
     a.th = in.tag.h; a.tw = in.tag.w;
     a.s_tag_y = (float)a.th / (float)a.H; a.s_tag_x = (float)a.tw / (float)a.W;
     axis_extents(a.W, TW, 0, a.tw, a.s_tag_x, 0, 0.f, &a.TG_C, nullptr);
@@ -630,12 +631,12 @@ int launch_nms(const HpdParams* p, const HpdBuffers* buf, float* nms_out, cudaSt
 
 int launch_resize(const HpdMap* in, int batch, int channels, float* out, int oh, int ow, cudaStream_t st) {
   if (!in || !in->ptr || !out || in->h < 1 || in->w < 1 || oh < 1 || ow < 1 || batch < 1 || channels < 1 ||
-      (long long)batch * channels > 65535 || oh > 65535) {
+      (long long)batch * channels > 65535 || oh > 65535 || in->dtype != HPD_F32) {
     set_error("hpd_resize_bilinear: bad arguments");
     return HPD_EINVAL;
   }
   const dim3 grid(((ow + 3) / 4 + 255) / 256, oh, batch * channels);
-  resize_kernel<<<grid, 256, 0, st>>>(in->ptr, in->stride_b, in->stride_c, channels, in->h, in->w, out, oh, ow,
+  resize_kernel<<<grid, 256, 0, st>>>((const float*)in->ptr, in->stride_b, in->stride_c, channels, in->h, in->w, out, oh, ow,
                                       (float)in->h / (float)oh, (float)in->w / (float)ow);
   count_launch();
   return check_launch("resize_kernel");

@@ -144,6 +144,33 @@ int hpd_resize_bilinear(const HpdMap* in, int batch, int channels, float* out, i
   return launch_resize(in, batch, channels, out, out_h, out_w, (cudaStream_t)stream);
 }
 
+int hpd_record_layout(const HpdParams* p, HpdRecordLayout* out) {
+  if (!p || !out) { set_error("NULL argument"); return HPD_EINVAL; }
+  if (p->num_kpts < 1 || p->num_kpts > HPD_MAX_KPTS || p->max_people < 1 || p->max_people > HPD_MAX_PEOPLE || p->emb < 1 ||
+      p->emb > HPD_MAX_EMB) {
+    set_error("hpd_record_layout: num_kpts / max_people / emb out of range");
+    return HPD_EINVAL;
+  }
+  *out = record_layout(p->num_kpts, p->max_people, p->emb);
+  return HPD_OK;
+}
+
+int hpd_multi_scale_size(int img_h, int img_w, int input_size, double current_scale, double min_scale,
+                         int32_t size_resized_wh[2], int32_t center_xy[2], double scale_wh[2]) {
+  return multi_scale_size(img_h, img_w, input_size, current_scale, min_scale, size_resized_wh, center_xy, scale_wh);
+}
+
+int hpd_get_affine_transform(const double center_xy[2], const double scale_wh[2], const int32_t output_size_wh[2],
+                             int inverse, double m_out[6]) {
+  return affine_transform_matrix(center_xy, scale_wh, output_size_wh, inverse, m_out);
+}
+
+int hpd_prepare_input(const HpdImage* images_host, int batch, float* out, int out_h, int out_w, const float mean[3],
+                      const float std_[3], void* stream) {
+  g_launches = 0;
+  return launch_prepare_input(images_host, batch, out, out_h, out_w, mean, std_, (cudaStream_t)stream);
+}
+
 int hpd_decode(const HpdParams* p, const HpdScaleInputs* scales, const HpdBuffers* buf, void* workspace,
                size_t workspace_bytes, void* stream) {
   g_launches = 0;

@@ -106,6 +106,21 @@ __device__ __forceinline__ void np_mean_vectors(const float* v, int n, int E, in
 }
 #endif  // __CUDACC__
 
+// ---- per-image result record (include/hpdecode.h: HpdRecordLayout) ------------------------------
+__host__ __device__ inline HpdRecordLayout record_layout(int K, int M, int E) {
+  HpdRecordLayout L;
+  L.coco_stride = 3 * K + 1;
+  L.reserved_ = 0;
+  long long off = 0;
+  L.off_coco = off;          off += 8LL * M * L.coco_stride;
+  L.off_poses = off;         off += 4LL * M * K * (3 + E);
+  L.off_person_scores = off; off += 4LL * M;
+  L.off_n_person = off;      off += 4;
+  L.off_flags = off;         off += 4;
+  L.row_bytes = (off + 7) / 8 * 8;
+  return L;
+}
+
 // ---- per-stage launchers (defined in the stage .cu files) -------------------------------------
 int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const HpdBuffers* buf, cudaStream_t st);
 int launch_nms(const HpdParams* p, const HpdBuffers* buf, float* nms_out, cudaStream_t st);
@@ -114,5 +129,10 @@ int launch_group(const HpdParams* p, const HpdBuffers* buf, cudaStream_t st);
 int launch_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* ws, size_t ws_bytes, cudaStream_t st);
 size_t refine_workspace_bytes(const HpdParams* p);
 int launch_resize(const HpdMap* in, int batch, int channels, float* out, int oh, int ow, cudaStream_t st);
+int launch_prepare_input(const HpdImage* images, int batch, float* out, int oh, int ow, const float* mean,
+                         const float* stdv, cudaStream_t st);
+int multi_scale_size(int h, int w, int input_size, double current_scale, double min_scale, int32_t* size_wh,
+                     int32_t* center_xy, double* scale_wh);
+int affine_transform_matrix(const double* center, const double* scale, const int32_t* out_wh, int inverse, double* m);
 
 }  // namespace hpd

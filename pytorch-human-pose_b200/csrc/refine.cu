@@ -270,24 +270,83 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
   }
 }
 
-__global__ void refine_apply_kernel(const float* __restrict__ agg_hm, int total, int K, int M, int E, int H, int W,
-                                    float* __restrict__ poses, RefineWs ws) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;   // (bk, slot)
-  if (i >= total) return;
-  const int bk = i / M, slot = i % M;
-  if (slot >= ws.miss_cnt[bk]) return;
-  const int b = bk / K, k = bk % K;
-  const int p = ws.miss_pid[(size_t)bk * M + slot];
-  const unsigned long long key = ws.keys[(size_t)bk * M + slot];
-  const int idx = (int)(~(unsigned)key);
-  const float* m = agg_hm + (size_t)bk * H * W;
-  const float val = m[idx];
-  if (!(val > 0.f)) return;     // grouping.py:248 (the pair is listed only if its score == 0)
-  const int y = idx / W, x = idx % W;
-  float fx = (float)x + 0.5f, fy = (float)y + 0.5f;
-  quarter_offset(m, H, W, x, y, fx, fy);
-  float* d = poses + (((size_t)b * M + p) * K + k) * (3 + E);
-  d[0] = fx; d[1] = fy; d[2] = val;
+// One block per image.  Phase 1 turns each listed pair's winning pixel into the refined joint (grouping.py:236-249).
+// Phase 2 -- the epilogue of the whole decode -- writes the image's result record (HpdRecordLayout): the grouped
+// joints / person scores / count / flags as they are, plus the COCO record of bin/eval.py:31-47 with the joints
+// back-projected to the raw image through the image's inverse affine matrix (results.py:158-171,189-201,244):
+// np.dot(M, [x, y, 1.0]) in float64 -- OpenBLAS's dgemv order fma(m2, 1, fma(m0, x, m1*y)) -- then rounded to
+// float32 because the reference writes it into a float32 array (results.py:165-170); the empty-scene fallback's
+// pseudo-person is float64 throughout with every score 0.01 (grouping.py:262-269), so its row stays unrounded.
+__global__ void __launch_bounds__(256) refine_apply_kernel(const float* __restrict__ agg_hm, int do_refine, int K, int M,
+                                                           int E, int H, int W, float* __restrict__ poses,
+                                                           const float* __restrict__ person_scores,
+                                                           const int32_t* __restrict__ n_person,
+                                                           const int32_t* __restrict__ flags, RefineWs ws,
+                                                           uint8_t* __restrict__ records,
+                                                           const double* __restrict__ inv_affine, HpdRecordLayout L,
+                                                           double fallback_score) {
+  const int b = blockIdx.x;
+  const int D = 3 + E;
+  if (do_refine) {
+    for (int i = threadIdx.x; i < K * M; i += blockDim.x) {   // (joint, slot)
+      const int k = i / M, slot = i - k * M;
+      const int bk = b * K + k;
+      if (slot >= ws.miss_cnt[bk]) continue;
+      const int p = ws.miss_pid[(size_t)bk * M + slot];
+      const unsigned long long key = ws.keys[(size_t)bk * M + slot];
+      const int idx = (int)(~(unsigned)key);
+      const float* m = agg_hm + (size_t)bk * H * W;
+      const float val = m[idx];
+      if (!(val > 0.f)) continue;     // grouping.py:248 (the pair is listed only if its score == 0)
+      const int y = idx / W, x = idx % W;
+      float fx = (float)x + 0.5f, fy = (float)y + 0.5f;
+      quarter_offset(m, H, W, x, y, fx, fy);
+      float* d = poses + (((size_t)b * M + p) * K + k) * D;
+      d[0] = fx; d[1] = fy; d[2] = val;
+    }
+  }
+  if (records == nullptr) return;
+  __syncthreads();
+  uint8_t* row = records + (size_t)b * L.row_bytes;
+  const int P = n_person[b];
+  const int flag = flags[b];
+  const float* src = poses + (size_t)b * M * K * D;
+  float* r_poses = (float*)(row + L.off_poses);
+  for (int i = threadIdx.x; i < M * K * D; i += blockDim.x) r_poses[i] = src[i];
+  float* r_scores = (float*)(row + L.off_person_scores);
+  for (int i = threadIdx.x; i < M; i += blockDim.x) r_scores[i] = person_scores[(size_t)b * M + i];
+  if (threadIdx.x == 0) {
+    *(int32_t*)(row + L.off_n_person) = P;
+    *(int32_t*)(row + L.off_flags) = flag;
+  }
+  double m0 = 1.0, m1 = 0.0, m2 = 0.0, m3 = 0.0, m4 = 1.0, m5 = 0.0;
+  if (inv_affine) {
+    const double* a = inv_affine + (size_t)b * 6;
+    m0 = a[0]; m1 = a[1]; m2 = a[2]; m3 = a[3]; m4 = a[4]; m5 = a[5];
+  }
+  const bool fallback = flag & 1;
+  double* coco = (double*)(row + L.off_coco);
+  for (int i = threadIdx.x; i < M * (K + 1); i += blockDim.x) {
+    const int p = i / (K + 1), k = i - p * (K + 1);
+    double* c = coco + (size_t)p * L.coco_stride;
+    if (k == K) {   // "score": obj_scores[i].mean().item(), bin/eval.py:45
+      c[3 * K] = p < P ? (fallback ? fallback_score : (double)person_scores[(size_t)b * M + p]) : 0.0;
+      continue;
+    }
+    double X = 0.0, Y = 0.0, V = 0.0;
+    if (p < P) {
+      const double x = (double)src[((size_t)p * K + k) * D], y = (double)src[((size_t)p * K + k) * D + 1];
+      if (inv_affine) {
+        X = fma(m2, 1.0, fma(m0, x, __dmul_rn(m1, y)));
+        Y = fma(m5, 1.0, fma(m3, x, __dmul_rn(m4, y)));
+      } else {
+        X = x; Y = y;
+      }
+      if (!fallback) { X = (double)(float)X; Y = (double)(float)Y; }
+      V = 1.0;
+    }
+    c[3 * k] = X; c[3 * k + 1] = Y; c[3 * k + 2] = V;
+  }
 }
 
 }  // namespace
@@ -319,17 +378,43 @@ int launch_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* wsp, s
                                               p->do_adjust, p->do_refine, buf->poses, buf->person_scores, ws);
   count_launch();
   int rc = check_launch("adjust_prepare_kernel");
-  if (rc || !p->do_refine) return rc;
-  const int nwords = H * wpr;
-  const dim3 grid((nwords + kScanWordsPerBlock - 1) / kScanWordsPerBlock, B * K);
-  for (int pass_id = 0; pass_id < 2; ++pass_id) {
-    refine_scan_kernel<<<grid, kScanWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->hm_wmax, buf->tag_bmin, buf->tag_bmax, buf->scores_k, pass_id,
-                                                         K, M, E, H, W, wpr, ws);
-    count_launch();
-    if ((rc = check_launch("refine_scan_kernel"))) return rc;
+  if (rc) return rc;
+  if (p->do_refine) {
+    const int nwords = H * wpr;
+    const dim3 grid((nwords + kScanWordsPerBlock - 1) / kScanWordsPerBlock, B * K);
+    for (int pass_id = 0; pass_id < 2; ++pass_id) {
+      refine_scan_kernel<<<grid, kScanWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->hm_wmax, buf->tag_bmin, buf->tag_bmax, buf->scores_k, pass_id,
+                                                           K, M, E, H, W, wpr, ws);
+      count_launch();
+      if ((rc = check_launch("refine_scan_kernel"))) return rc;
+    }
   }
-  const int total = B * K * M;
-  refine_apply_kernel<<<(total + 255) / 256, 256, 0, st>>>(buf->agg_hm, total, K, M, E, H, W, buf->poses, ws);
+  if (!p->do_refine && !buf->records) return HPD_OK;
+  if (buf->records && (!buf->flags || (uintptr_t)buf->records % 8 != 0)) {
+    set_error("hpd_adjust_refine: records need flags and an 8-byte aligned buffer");
+    return HPD_EINVAL;
+  }
+  // the fallback pseudo-person's score: np.mean of K float64 copies of 0.01 (numpy's pairwise-8 order)
+  double fb_score;
+  {
+    const double v = 0.01;
+    if (K < 8) {
+      fb_score = -0.0;
+      for (int i = 0; i < K; ++i) fb_score += v;
+    } else {
+      double r[8];
+      for (int j = 0; j < 8; ++j) r[j] = v;
+      int i = 8;
+      for (; i < K - (K % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] += v;
+      fb_score = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+      for (; i < K; ++i) fb_score += v;
+    }
+    fb_score /= (double)K;
+  }
+  refine_apply_kernel<<<B, 256, 0, st>>>(buf->agg_hm, p->do_refine, K, M, E, H, W, buf->poses, buf->person_scores,
+                                         buf->n_person, buf->flags, ws, buf->records, buf->inv_affine,
+                                         record_layout(K, M, E), fb_score);
   count_launch();
   return check_launch("refine_apply_kernel");
 }

@@ -10,7 +10,8 @@ HPD_MAX_KPTS = 32
 HPD_MAX_PEOPLE = 32
 HPD_MAX_EMB = 2
 HPD_MAX_SCALES = 4
-HPD_ABI_VERSION = 1
+HPD_ABI_VERSION = 2
+HPD_F32, HPD_F16 = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libhpdecode.so")
@@ -18,12 +19,13 @@ LIB_PATH = os.path.join(_HERE, "libhpdecode.so")
 EXPORTS = (
     "hpd_abi_version", "hpd_last_error_string", "hpd_workspace_bytes", "hpd_aggregate_nms", "hpd_nms",
     "hpd_topk", "hpd_group", "hpd_adjust_refine", "hpd_decode", "hpd_last_launch_count", "hpd_resize_bilinear",
+    "hpd_record_layout", "hpd_multi_scale_size", "hpd_get_affine_transform", "hpd_prepare_input",
 )
 
 
 class HpdMap(ctypes.Structure):
     _fields_ = [("ptr", ctypes.c_void_p), ("stride_b", ctypes.c_int64), ("stride_c", ctypes.c_int64),
-                ("h", ctypes.c_int32), ("w", ctypes.c_int32)]
+                ("h", ctypes.c_int32), ("w", ctypes.c_int32), ("dtype", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
 
 
 class HpdScaleInputs(ctypes.Structure):
@@ -43,7 +45,18 @@ class HpdParams(ctypes.Structure):
 class HpdBuffers(ctypes.Structure):
     _fields_ = [(n, ctypes.c_void_p) for n in (
         "agg_hm", "agg_tags", "nms_mask", "nms_wmax", "hm_wmax", "scores_k", "idx_k", "coords_k", "tags_k",
-        "poses", "person_scores", "n_person", "flags", "tag_bmin", "tag_bmax")]
+        "poses", "person_scores", "n_person", "flags", "tag_bmin", "tag_bmax", "records", "inv_affine")]
+
+
+class HpdRecordLayout(ctypes.Structure):
+    _fields_ = [("row_bytes", ctypes.c_int64), ("off_coco", ctypes.c_int64), ("off_poses", ctypes.c_int64),
+                ("off_person_scores", ctypes.c_int64), ("off_n_person", ctypes.c_int64), ("off_flags", ctypes.c_int64),
+                ("coco_stride", ctypes.c_int32), ("reserved_", ctypes.c_int32)]
+
+
+class HpdImage(ctypes.Structure):
+    _fields_ = [("ptr", ctypes.c_void_p), ("stride_row", ctypes.c_int64), ("h", ctypes.c_int32), ("w", ctypes.c_int32),
+                ("m", ctypes.c_double * 6)]
 
 
 class HpdError(RuntimeError):
@@ -76,6 +89,12 @@ def lib():
     L.hpd_decode.argtypes = [P, S, B, V, ctypes.c_size_t, V]
     L.hpd_resize_bilinear.argtypes = [ctypes.POINTER(HpdMap), ctypes.c_int, ctypes.c_int, V, ctypes.c_int,
                                       ctypes.c_int, V]
+    I32P, F64P, F32P = ctypes.POINTER(ctypes.c_int32), ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_float)
+    L.hpd_record_layout.argtypes = [P, ctypes.POINTER(HpdRecordLayout)]
+    L.hpd_multi_scale_size.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, I32P,
+                                       I32P, F64P]
+    L.hpd_get_affine_transform.argtypes = [F64P, F64P, I32P, ctypes.c_int, F64P]
+    L.hpd_prepare_input.argtypes = [ctypes.POINTER(HpdImage), ctypes.c_int, V, ctypes.c_int, ctypes.c_int, F32P, F32P, V]
     for n in EXPORTS:
         if n not in ("hpd_last_error_string",):
             getattr(L, n).restype = ctypes.c_int

@@ -17,6 +17,48 @@ import torch
 from . import ops
 
 
+class Records:
+    """Host view of the per-image result records written by the decode's last kernel (HpdRecordLayout,
+    include/hpdecode.h): ``raw`` is the uint8 [B,row_bytes] array of ONE device->host copy; the fields are
+    zero-copy NumPy views into it."""
+
+    def __init__(self, raw: np.ndarray, M: int, K: int, E: int):
+        L = ops.record_layout(K, M, E)
+        raw = np.ascontiguousarray(raw, np.uint8).reshape(-1, L.row_bytes)
+        self.raw, self.M, self.K, self.E = raw, M, K, E
+        B, D, C = raw.shape[0], 3 + E, L.coco_stride
+
+        def view(off, dtype, shape, strides):
+            return np.ndarray((B,) + shape, dtype, raw, offset=off, strides=(L.row_bytes,) + strides)
+
+        self.coco = view(L.off_coco, np.float64, (M, C), (8 * C, 8))                       # (x, y, 1)*K, score
+        self.poses = view(L.off_poses, np.float32, (M, K, D), (4 * K * D, 4 * D, 4))       # grouped joints
+        self.person_scores = view(L.off_person_scores, np.float32, (M,), (4,))
+        self.n_person = view(L.off_n_person, np.int32, (), ())
+        self.flags = view(L.off_flags, np.int32, (), ())
+
+    def __len__(self):
+        return self.raw.shape[0]
+
+    def image(self, b: int) -> Tuple[np.ndarray, np.ndarray]:
+        """(grouped_joints [P,K,3+E], person_scores [P]) -- MPPEHeatmapParser.parse's return for image b."""
+        P = int(self.n_person[b])
+        return _finish(self.poses[b, :P].copy(), self.person_scores[b, :P].copy(), int(self.flags[b]) & 1)
+
+    def final_coords(self, b: int) -> np.ndarray:
+        """kpts_coords [P,K,2] back-projected to the raw image (results.py:244): float32 like the reference's
+        array, float64 for the empty-scene fallback's pseudo-person."""
+        P = int(self.n_person[b])
+        xy = self.coco[b, :P, : 3 * self.K].reshape(P, self.K, 3)[..., :2]
+        return xy.copy() if int(self.flags[b]) & 1 else xy.astype(np.float32)
+
+    def coco_records(self, b: int, image_id: int) -> List[dict]:
+        """The COCO result dicts evaluate_dataset appends for image b (bin/eval.py:31-47)."""
+        P = int(self.n_person[b])
+        return [{"image_id": int(image_id), "category_id": 1, "keypoints": self.coco[b, p, : 3 * self.K].tolist(),
+                 "score": float(self.coco[b, p, 3 * self.K])} for p in range(P)]
+
+
 class DecodeResult:
     """Device-side result of one batch; ``to_numpy`` gives the reference's per-image return values."""
 
@@ -28,30 +70,26 @@ class DecodeResult:
         self.person_scores = bufs.person_scores
         self.n_person = bufs.n_person
         self.flags = bufs.flags
+        self.records = bufs.records        # [B,row_bytes] uint8, written by the last kernel's epilogue
 
     def packed(self) -> torch.Tensor:
-        """One device tensor [B, M*K*(3+E) + M + 2] holding poses, person scores, count and flag,
-        so the device->host read of a batch is a single copy."""
-        B = self.poses.shape[0]
-        return torch.cat([self.poses.reshape(B, -1), self.person_scores,
-                          self.n_person.to(torch.float32)[:, None], self.flags.to(torch.float32)[:, None]], dim=1)
+        """The device tensor that holds everything a caller reads after a decode (one row per image):
+        no ATen op runs here, the kernels wrote this layout themselves."""
+        return self.records
+
+    def host(self) -> "Records":
+        B, M, K, D = self.poses.shape
+        return Records(self.records.cpu().numpy(), M, K, D - 3)
 
     @staticmethod
     def unpack(packed: np.ndarray, M: int, K: int, E: int) -> List[Tuple[np.ndarray, np.ndarray]]:
-        out = []
-        D = 3 + E
-        for row in packed:
-            P = int(row[-2])
-            fb = int(row[-1]) & 1
-            poses = row[: M * K * D].reshape(M, K, D)[:P].copy()
-            scores = row[M * K * D: M * K * D + M][:P].copy()
-            out.append(_finish(poses, scores, fb))
-        return out
+        rec = Records(packed, M, K, E)
+        return [rec.image(b) for b in range(len(rec))]
 
     def to_numpy(self) -> List[Tuple[np.ndarray, np.ndarray]]:
         """[(grouped_joints [P,K,3+E], person_scores [P]) per image] -- MPPEHeatmapParser.parse's return."""
-        B, M, K, D = self.poses.shape
-        return self.unpack(self.packed().cpu().numpy(), M, K, D - 3)
+        rec = self.host()
+        return [rec.image(b) for b in range(len(rec))]
 
 
 def _finish(poses: np.ndarray, scores: np.ndarray, fallback: int):
@@ -94,8 +132,15 @@ class BottomUpDecoder:
             slots[slot] = ops.DecodeBuffers(B, self.num_kpts, H, W, E, self.max_num_people, self.device)
         return slots[slot]
 
+    def _set_inv_affine(self, bufs: ops.DecodeBuffers, inv_affine):
+        if inv_affine is None:
+            bufs.inv_affine = None
+            return
+        t = inv_affine if isinstance(inv_affine, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(inv_affine, np.float64))
+        bufs.inv_affine = t.reshape(-1, 6).to(self.device, torch.float64, non_blocking=True).contiguous()
+
     def decode(self, scales: Sequence[dict], out_hw: Tuple[int, int], tag_scale: int = 0,
-               tags_preflipped: bool = False, slot: int = 0) -> DecodeResult:
+               tags_preflipped: bool = False, slot: int = 0, inv_affine=None) -> DecodeResult:
         """scales: one dict per test scale with CUDA float32 tensors hm_lo, hm_hi, tag [B,K,h,w] and,
         for the flip test, hm_lo_f, hm_hi_f, tag_f (raw outputs of the flipped forward).
 
@@ -106,6 +151,7 @@ class BottomUpDecoder:
         B = scales[0]["hm_lo"].shape[0]
         E = 2 if scales[tag_scale].get("tag_f") is not None else 1
         bufs = self.buffers(B, H, W, E, slot)
+        self._set_inv_affine(bufs, inv_affine)     # float64 [B,6]: back-projection of the records' COCO section
         params = ops.make_params(B, self.num_kpts, H, W, E, self.max_num_people, self.det_thr, self.tag_thr,
                                  self.adjust, self.refine, len(scales), tag_scale, tags_preflipped=tags_preflipped)
         ops.run_decode(scales, bufs, params)
@@ -126,34 +172,43 @@ class BottomUpDecoder:
 class DecodePipeline:
     """Keeps ``depth`` batches in flight on one GPU.
 
-    The path has one bandwidth-bound kernel (fused aggregation + NMS) followed by three latency-bound
-    ones (top-k, grouping, refine) that occupy a handful of SMs each.  Every lane owns a buffer set,
-    a normal-priority stream for the aggregation kernel and a high-priority stream for the rest, so
-    batch i+1's aggregation overlaps batch i's tail and the small kernels get SM slots as soon as
-    they are runnable.  ``submit`` returns the lane's DecodeResult; it stays valid until the lane is
-    reused ``depth`` submits later (call ``result.ready.synchronize()`` or ``drain()`` before reading).
-    Lifetime contract for the inputs: ``submit`` records their use on the lane's stream
-    (``Tensor.record_stream``), so the caller may drop them as soon as it returns.
+    The path has one bandwidth-bound kernel (fused aggregation + NMS) followed by latency-bound ones (top-k,
+    grouping, refine) that occupy a handful of SMs each.  Every lane owns a buffer set and a stream, so batch i+1's
+    aggregation overlaps batch i's tail.  ``submit`` returns the lane's DecodeResult; it stays valid until the lane
+    is reused ``depth`` submits later (call ``result.ready.synchronize()`` or ``drain()`` before reading).
+    Lifetime contract for the inputs: ``submit`` records their use on the lane's stream (``Tensor.record_stream``),
+    so the caller may drop them as soon as it returns.
+
+    ``records_ring``: an optional uint8 tensor [depth, B, row_bytes]; lane i's result records are then written
+    straight into ``records_ring[i]`` by the decode's last kernel, so consecutive lanes form one contiguous block
+    (one gather / one device->host copy for several batches).
+    ``use_graphs``: the launches of a lane are captured in a CUDA graph per (input pointers, shape) and replayed --
+    for small per-GPU batches, where seven launches plus their ctypes marshalling would cost more host time than
+    the kernels take.  The inputs must then stay at the same addresses between submits.
     """
 
-    def __init__(self, decoder: "BottomUpDecoder", depth: int = 3, split_priority: bool = False):
+    STAGES = ("aggregate_nms", "topk", "group", "adjust_refine")
+
+    def __init__(self, decoder: "BottomUpDecoder", depth: int = 3, records_ring: Optional[torch.Tensor] = None,
+                 use_graphs: bool = False):
         self.dec = decoder
         self.depth = max(1, depth)
-        dev = decoder.device
-        self.lanes = []
-        for i in range(self.depth):
-            s_agg = torch.cuda.Stream(device=dev, priority=0)
-            # split_priority: the tail kernels run on their own high-priority stream (measured slightly
-            # slower on B200 than one stream per lane, so it is off by default)
-            s_tail = torch.cuda.Stream(device=dev, priority=-1) if split_priority else s_agg
-            self.lanes.append({"slot": i, "s_agg": s_agg, "s_tail": s_tail, "agg_done": torch.cuda.Event(),
-                               "ready": torch.cuda.Event(), "used": False})
+        self.records_ring = records_ring
+        self.use_graphs = use_graphs
+        self.graph_replays = 0
+        self.lanes = [{"slot": i, "stream": torch.cuda.Stream(device=decoder.device), "ready": torch.cuda.Event(),
+                       "used": False, "graphs": {}, "gate": None} for i in range(self.depth)]
         self._next = 0
 
+    def _launch(self, ln, bufs, params, scales):
+        for st in self.STAGES:
+            ops.run_stage(st, bufs, params, scales=scales if st == "aggregate_nms" else None)
+
     def submit(self, scales: Sequence[dict], out_hw: Tuple[int, int], tag_scale: int = 0, before_agg=None,
-               after_tail=None) -> DecodeResult:
-        """Enqueue one batch.  ``before_agg(lane)`` / ``after_tail(lane, result)`` run on the lane's streams
-        (e.g. the H2D copies of the inputs and the D2H copy of the packed poses)."""
+               after_tail=None, inv_affine=None) -> DecodeResult:
+        """Enqueue one batch.  ``before_agg(lane)`` / ``after_tail(lane, result)`` run on the lane's stream
+        (e.g. the H2D copies of the inputs and the D2H copy of the records).  A lane's ``gate`` event, if a
+        callback set one (say, a gather that still reads the lane's records), is waited for before reuse."""
         ln = self.lanes[self._next]
         self._next = (self._next + 1) % self.depth
         H, W = out_hw
@@ -161,31 +216,51 @@ class DecodePipeline:
         E = 2 if scales[tag_scale].get("tag_f") is not None else 1
         d = self.dec
         bufs = d.buffers(B, H, W, E, slot=ln["slot"])
+        if self.records_ring is not None:
+            bufs.records = self.records_ring[ln["slot"]]
         params = ops.make_params(B, d.num_kpts, H, W, E, d.max_num_people, d.det_thr, d.tag_thr, d.adjust, d.refine,
                                  len(scales), tag_scale)
         cur = torch.cuda.current_stream(d.device)
-        ln["s_agg"].wait_stream(cur)
+        st = ln["stream"]
+        if inv_affine is not None or bufs.inv_affine is not None:
+            d._set_inv_affine(bufs, inv_affine)
+            if bufs.inv_affine is not None:
+                bufs.inv_affine.record_stream(st)
+        st.wait_stream(cur)
         # The inputs were allocated on the caller's stream but are read on the lane's: tell the caching
         # allocator, or a caller that drops them right after submit() (net outputs -> submit -> next forward)
         # could get their memory back while the aggregation kernel is still reading it.
         for s in scales:
             for t in s.values():
                 if t is not None and t.is_cuda:
-                    t.record_stream(ln["s_agg"])
-        with torch.cuda.stream(ln["s_agg"]):
+                    t.record_stream(st)
+        res = DecodeResult(bufs)
+        with torch.cuda.stream(st):
             if ln["used"]:
-                ln["s_agg"].wait_event(ln["ready"])     # the lane's previous batch has been consumed
+                st.wait_event(ln["ready"])             # the lane's previous batch has been consumed
+            if ln["gate"] is not None:
+                st.wait_event(ln["gate"])
             if before_agg is not None:
                 scales = before_agg(ln) or scales      # tensors made here belong to the lane's stream already
-            ops.run_stage("aggregate_nms", bufs, params, scales=scales)
-            if ln["s_tail"] is not ln["s_agg"]:
-                ln["agg_done"].record()
-        res = DecodeResult(bufs)
-        with torch.cuda.stream(ln["s_tail"]):
-            if ln["s_tail"] is not ln["s_agg"]:
-                ln["s_tail"].wait_event(ln["agg_done"])
-            for st in ("topk", "group", "adjust_refine"):
-                ops.run_stage(st, bufs, params)
+            if self.use_graphs:
+                key = (tuple(t.data_ptr() for s in scales for t in s.values() if t is not None), B, H, W, tag_scale,
+                       bufs.records.data_ptr(), 0 if bufs.inv_affine is None else bufs.inv_affine.data_ptr())
+                g = ln["graphs"].get(key)
+                if g is None:
+                    self._launch(ln, bufs, params, scales)      # eager once: workspace, shared-memory opt-ins
+                    st.synchronize()
+                    g = torch.cuda.CUDAGraph()
+                    ops.launches_in_last_capture()
+                    with torch.cuda.graph(g, stream=st):
+                        self._launch(ln, bufs, params, scales)
+                    n_captured = ops.launches_in_last_capture()
+                    ops.add_launches(-n_captured)              # captured, not executed
+                    g = ln["graphs"][key] = (g, n_captured)
+                g[0].replay()
+                ops.add_launches(g[1])
+                self.graph_replays += 1
+            else:
+                self._launch(ln, bufs, params, scales)
             if after_tail is not None:
                 after_tail(ln, res)
             ln["ready"].record()
@@ -199,3 +274,5 @@ class DecodePipeline:
         for ln in self.lanes:
             if ln["used"]:
                 cur.wait_event(ln["ready"])
+            if ln["gate"] is not None:
+                cur.wait_event(ln["gate"])

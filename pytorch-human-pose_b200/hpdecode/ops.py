@@ -19,7 +19,7 @@ import torch
 from torch import Tensor
 
 from . import _lib
-from ._lib import HpdBuffers, HpdMap, HpdParams, HpdScaleInputs
+from ._lib import HpdBuffers, HpdImage, HpdMap, HpdParams, HpdRecordLayout, HpdScaleInputs
 
 COCO_FLIP_INDEX = [0, 2, 1, 4, 3, 6, 5, 8, 7, 10, 9, 12, 11, 14, 13, 16, 15]  # transforms.py:11
 JOINTS_ORDER_17 = [0, 1, 2, 3, 4, 5, 6, 11, 12, 7, 8, 9, 10, 13, 14, 15, 16]   # grouping.py:63-65
@@ -73,8 +73,27 @@ def make_params(B: int, K: int, H: int, W: int, E: int, M: int, det_thr: float, 
     return p
 
 
+_layouts = {}
+
+
+def record_layout(K: int, M: int, E: int) -> HpdRecordLayout:
+    """hpd_record_layout for (num_kpts, max_people, emb): byte offsets of one image's result record."""
+    key = (K, M, E)
+    if key not in _layouts:
+        p = HpdParams()
+        p.num_kpts, p.max_people, p.emb = K, M, E
+        L = HpdRecordLayout()
+        _lib.check(_lib.lib().hpd_record_layout(ctypes.byref(p), ctypes.byref(L)), "hpd_record_layout")
+        _layouts[key] = L
+    return _layouts[key]
+
+
 class DecodeBuffers:
-    """Device buffers of one decode call (HpdBuffers).  Re-usable across calls of the same shape."""
+    """Device buffers of one decode call (HpdBuffers).  Re-usable across calls of the same shape.
+
+    ``records`` [B,row_bytes] uint8 receives one result record per image (HpdRecordLayout) from the epilogue of
+    the last kernel; ``inv_affine`` (optional float64 [B,6] on the device) is the per-image matrix the COCO
+    section's coordinates are back-projected with (None = network-input coordinates)."""
 
     def __init__(self, B: int, K: int, H: int, W: int, E: int, M: int, device, agg_hm: Optional[Tensor] = None,
                  agg_tags: Optional[Tensor] = None):
@@ -97,6 +116,8 @@ class DecodeBuffers:
         self.person_scores = torch.empty((B, M), **f32)
         self.n_person = torch.empty((B,), **i32)
         self.flags = torch.empty((B,), **i32)
+        self.records = torch.empty((B, record_layout(K, M, E).row_bytes), device=device, dtype=torch.uint8)
+        self.inv_affine = None
         self.workspace = None
 
     @classmethod
@@ -115,6 +136,7 @@ class DecodeBuffers:
         self.poses = torch.empty((B, M, K, 3 + E), device=dev, dtype=torch.float32)
         self.n_person = torch.empty((B,), device=dev, dtype=torch.int32)
         self.flags = torch.empty((B,), device=dev, dtype=torch.int32)
+        self.records = self.inv_affine = None
         self.workspace = None
         return self
 
@@ -122,6 +144,10 @@ class DecodeBuffers:
         s = HpdBuffers()
         for name, _ in HpdBuffers._fields_:
             t = getattr(self, name)
+            if t is None:
+                continue
+            if name == "inv_affine" and (t.dtype != torch.float64 or t.numel() != 6 * self.shape[0] or not t.is_cuda):
+                raise _lib.HpdError("inv_affine must be a CUDA float64 tensor [B,6]")
             if not t.is_contiguous():
                 raise _lib.HpdError(f"buffer {name} must be contiguous")
             setattr(s, name, t.data_ptr())
@@ -150,9 +176,27 @@ def _scales_struct(scales: Sequence[dict]):
     return arr, keep
 
 
+_capture_launches = 0
+
+
 def _count(L):
+    global _launches, _capture_launches
+    n = L.hpd_last_launch_count()
+    _launches += n
+    _capture_launches += n
+
+
+def launches_in_last_capture() -> int:
+    """Launches enqueued since the previous call of this function (DecodePipeline brackets a graph capture with
+    two calls and books that many launches per replay)."""
+    global _capture_launches
+    n, _capture_launches = _capture_launches, 0
+    return n
+
+
+def add_launches(n: int):
     global _launches
-    _launches += L.hpd_last_launch_count()
+    _launches += n
 
 
 # ------------------------------------------------------------------------------------------------
@@ -309,6 +353,37 @@ def resize_bilinear_op(x: Tensor, out_h: int, out_w: int) -> Tensor:
     return out
 
 
+@torch.library.custom_op("hpd::prepare_input", mutates_args=())
+def prepare_input_op(images: Sequence[Tensor], matrices: Tensor, out_h: int, out_w: int, mean: Sequence[float],
+                     std: Sequence[float]) -> Tensor:
+    """cv2.warpAffine(image, M, (out_w, out_h)) + ToTensor + Normalize (utils.py:96, model.py:45-50) for a batch of
+    uint8 [h,w,3] CUDA images; ``matrices``: float64 [B,6] on the HOST (the forward 2x3 matrices).  -> [B,3,out_h,out_w]."""
+    if len(images) == 0 or matrices.is_cuda or matrices.dtype != torch.float64 or matrices.numel() != 6 * len(images):
+        raise _lib.HpdError("prepare_input: need >= 1 image and a host float64 [B,6] matrix tensor")
+    dev = images[0].device
+    arr = (HpdImage * len(images))()
+    mats = matrices.reshape(-1, 6).tolist()
+    for i, t in enumerate(images):
+        if not t.is_cuda or t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3 or t.stride(2) != 1 or t.stride(1) != 3:
+            raise _lib.HpdError("prepare_input: image %d must be a CUDA uint8 [h,w,3] tensor with packed pixels" % i)
+        arr[i].ptr, arr[i].stride_row, arr[i].h, arr[i].w = t.data_ptr(), t.stride(0), t.shape[0], t.shape[1]
+        for j in range(6):
+            arr[i].m[j] = mats[i][j]
+    out = torch.empty((len(images), 3, out_h, out_w), device=dev, dtype=torch.float32)
+    mean_c, std_c = (ctypes.c_float * 3)(*mean), (ctypes.c_float * 3)(*std)
+    L = _lib.lib()
+    with torch.cuda.device(dev):
+        rc = L.hpd_prepare_input(arr, len(images), out.data_ptr(), out_h, out_w, mean_c, std_c, _stream_ptr(dev))
+    _lib.check(rc, "hpd_prepare_input")
+    _count(L)
+    return out
+
+
+@prepare_input_op.register_fake
+def _(images, matrices, out_h, out_w, mean, std):
+    return images[0].new_empty((len(images), 3, out_h, out_w), dtype=torch.float32)
+
+
 @resize_bilinear_op.register_fake
 def _(x, out_h, out_w):
     return x.new_empty((x.shape[0], x.shape[1], out_h, out_w))
@@ -324,3 +399,32 @@ def _(hm_lo, hm_hi, tag, hm_lo_f, hm_hi_f, tag_f, out_h, out_w, max_people, det_
     i = lambda *s: hm_lo[0].new_empty(s, dtype=torch.int32)
     return [f(B, K, out_h, out_w), f(B, K, out_h, out_w, E), f(B, M, K, 3 + E), f(B, M), i(B), i(B), f(B, K, M),
             i(B, K, M), i(B, K, M, 2), f(B, K, M, E)]
+
+
+@parse_op.register_fake
+def _(agg_hm, agg_tags, max_people, det_thr, tag_thr, adjust, refine):
+    B, K = agg_hm.shape[:2]
+    E, M = agg_tags.shape[4], max_people
+    f = lambda *s: agg_hm.new_empty(s)
+    i = lambda *s: agg_hm.new_empty(s, dtype=torch.int32)
+    return [f(B, M, K, 3 + E), f(B, M), i(B), i(B), f(B, K, M), i(B, K, M), i(B, K, M, 2), f(B, K, M, E)]
+
+
+@nms_op.register_fake
+def _(hm):
+    return torch.empty_like(hm)
+
+
+@topk_op.register_fake
+def _(agg_hm, agg_tags, max_people):
+    B, K = agg_hm.shape[:2]
+    E, M = agg_tags.shape[4], max_people
+    return [agg_hm.new_empty((B, K, M, E)), agg_hm.new_empty((B, K, M, 2), dtype=torch.int32), agg_hm.new_empty((B, K, M)),
+            agg_hm.new_empty((B, K, M), dtype=torch.int32)]
+
+
+@group_op.register_fake
+def _(tags_k, coords_k, scores_k, det_thr, tag_thr, out_h, out_w):
+    B, K, M, E = tags_k.shape
+    return [tags_k.new_empty((B, M, K, 3 + E)), tags_k.new_empty((B,), dtype=torch.int32),
+            tags_k.new_empty((B,), dtype=torch.int32)]

@@ -45,3 +45,16 @@ def gather_packed_equal(packed: torch.Tensor, out: Optional[torch.Tensor], dst: 
         return out
     dist.gather(packed, None, dst=dst, group=group)
     return None
+
+
+def gather_rows(block: torch.Tensor, out: Optional[torch.Tensor], dst: int = 0, group=None):
+    """The bench's gather: every rank contributes one flat tensor of n elements (the result records of one or
+    several batches), ``out`` [world, n] on ``dst`` receives rank r's block in row r.  One collective, issued on
+    the CURRENT stream (the caller puts it on a communication stream of its own)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return block
+    if dist.get_rank(group) == dst:
+        dist.gather(block, list(out.unbind(0)), dst=dst, group=group)
+        return out
+    dist.gather(block, None, dst=dst, group=group)
+    return None

@@ -32,14 +32,17 @@ def test_library_exports_every_declared_symbol():
 def test_ctypes_structs_match_c_layout(tmp_path):
     from hpdecode import _lib
     probe = tmp_path / "probe.c"
-    probe.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hpdecode.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu\\n",'
+    probe.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "hpdecode.h"\nint main(){printf("%zu %zu %zu %zu %zu %zu %zu %zu %zu %zu\\n",'
                      "sizeof(HpdMap),sizeof(HpdScaleInputs),sizeof(HpdParams),sizeof(HpdBuffers),"
-                     "offsetof(HpdParams,det_thr),offsetof(HpdParams,joints_order));return 0;}\n")
+                     "offsetof(HpdParams,det_thr),offsetof(HpdParams,joints_order),sizeof(HpdRecordLayout),sizeof(HpdImage),"
+                     "offsetof(HpdImage,m),offsetof(HpdBuffers,records));return 0;}\n")
     exe = tmp_path / "probe"
     subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(probe), "-o", str(exe)])
     got = [int(x) for x in subprocess.check_output([str(exe)]).split()]
     want = [ctypes.sizeof(_lib.HpdMap), ctypes.sizeof(_lib.HpdScaleInputs), ctypes.sizeof(_lib.HpdParams),
-            ctypes.sizeof(_lib.HpdBuffers), _lib.HpdParams.det_thr.offset, _lib.HpdParams.joints_order.offset]
+            ctypes.sizeof(_lib.HpdBuffers), _lib.HpdParams.det_thr.offset, _lib.HpdParams.joints_order.offset,
+            ctypes.sizeof(_lib.HpdRecordLayout), ctypes.sizeof(_lib.HpdImage), _lib.HpdImage.m.offset,
+            _lib.HpdBuffers.records.offset]
     assert got == want
 
 

@@ -26,19 +26,35 @@ def test_synth_is_deterministic_and_shaped():
     assert [s["hm_hi"].shape[-1] for s in ms] == [160, 320, 480]
 
 
-def test_unpack_and_fallback_dtype():
+def test_records_view_and_fallback_dtype():
+    """Records: the host view of the device-written result records (HpdRecordLayout)."""
+    from hpdecode import ops
+    from hpdecode.decoder import Records
     M, K, E = 4, 17, 2
     D = 3 + E
-    row = np.zeros(M * K * D + M + 2, np.float32)
-    row[: 2 * K * D] = np.arange(2 * K * D)
-    row[M * K * D: M * K * D + 2] = [0.5, 0.25]
-    row[-2] = 2
-    poses, scores = DecodeResult.unpack(row[None], M, K, E)[0]
+    L = ops.record_layout(K, M, E)
+    assert L.coco_stride == 3 * K + 1 and L.row_bytes % 8 == 0 and L.off_coco == 0
+    assert L.off_poses == 8 * M * (3 * K + 1) and L.off_person_scores == L.off_poses + 4 * M * K * D
+    raw = np.zeros((2, L.row_bytes), np.uint8)
+    rec = Records(raw, M, K, E)
+    rec.poses[1, :2] = np.arange(2 * K * D, dtype=np.float32).reshape(2, K, D)
+    rec.person_scores[1, :2] = [0.5, 0.25]
+    rec.n_person[1] = 2
+    rec.coco[1, 0, :3] = [10.5, 20.25, 1.0]
+    rec.coco[1, 0, 3 * K] = 0.5
+    again = Records(raw.copy(), M, K, E)                       # the views write through to the raw bytes
+    poses, scores = again.image(1)
     assert poses.shape == (2, K, D) and poses.dtype == np.float32 and list(scores) == [0.5, 0.25]
+    assert poses[1, 3, 2] == float(K * D + 3 * D + 2)
+    assert again.final_coords(1).dtype == np.float32 and again.final_coords(1)[0, 0].tolist() == [10.5, 20.25]
+    recs = again.coco_records(1, 42)
+    assert len(recs) == 2 and recs[0]["image_id"] == 42 and recs[0]["category_id"] == 1 and recs[0]["score"] == 0.5
+    assert len(recs[0]["keypoints"]) == 3 * K and recs[0]["keypoints"][:3] == [10.5, 20.25, 1.0]
+    assert again.image(0)[0].shape == (0, K, D) and DecodeResult.unpack(raw, M, K, E)[1][0].shape == (2, K, D)
     fb = np.zeros((1, K, D), np.float32)
     fb[..., 2] = np.float32(0.01)
-    p, s = _finish(fb, np.zeros(1, np.float32), 1)
-    assert p.dtype == np.float64 and p[0, 0, 2] == 0.01 and s[0] == np.full((1, K), 0.01).mean(1)[0]
+    p, s_ = _finish(fb, np.zeros(1, np.float32), 1)
+    assert p.dtype == np.float64 and p[0, 0, 2] == 0.01 and s_[0] == np.full((1, K), 0.01).mean(1)[0]
 
 
 def test_shard_range_partitions():
@@ -110,23 +126,16 @@ def test_gather_packed_equal_world2_gloo():
     assert np.array_equal(got, np.concatenate([base, base + 100]))
 
 
-def test_back_projection_and_coco_records():
-    """results.py:158-201 + eval.py:31-47 on the host: identity-like transform keeps coordinates, records
-    have the COCO layout."""
-    from hpdecode.coco import batch_to_coco, coco_records
-    from hpdecode.transforms import affine_transform, get_affine_transform
-    m = get_affine_transform((256, 256), (512.0, 512.0), 0, (512, 512), inverse=True)
-    assert m.shape == (2, 3) and np.allclose(affine_transform([10.0, 20.0], m), [10.0, 20.0], atol=1e-4)
-    m2 = get_affine_transform((320, 240), (640.0, 480.0), 0, (512, 384), inverse=True)      # 0.8x network input
-    assert np.allclose(affine_transform([256.0, 192.0], m2), [320.0, 240.0], atol=1e-3)
-    grouped = np.zeros((2, 17, 4), np.float32)
-    grouped[..., 0] = 100.0
-    grouped[..., 1] = 50.0
-    recs = batch_to_coco([7], [(grouped, np.array([0.5, 0.25], np.float32))], [(256, 256)], [(512.0, 512.0)], (512, 512))
+def test_result_to_coco_layout():
+    """bin/eval.py:31-47 from a result object (the reference's per-image path)."""
+    from types import SimpleNamespace
+    from hpdecode.coco import image_id_of, result_to_coco
+    coords = np.zeros((2, 17, 2), np.float32)
+    coords[..., 0], coords[..., 1] = 100.5, 50.25
+    recs = result_to_coco(7, SimpleNamespace(kpts_coords=coords, obj_scores=np.array([0.5, 0.25], np.float32)))
     assert len(recs) == 2 and recs[0]["image_id"] == 7 and recs[0]["category_id"] == 1
-    assert len(recs[0]["keypoints"]) == 51 and recs[0]["keypoints"][2] == 1 and abs(recs[0]["keypoints"][0] - 100.0) < 1e-3
-    assert recs[1]["score"] == 0.25
-    assert coco_records(1, np.zeros((0, 17, 2)), np.zeros((0,))) == []
+    assert len(recs[0]["keypoints"]) == 51 and recs[0]["keypoints"][:3] == [100.5, 50.25, 1.0] and recs[1]["score"] == 0.25
+    assert image_id_of("/data/coco/images/val2017/000000000139.jpg") == 139
 
 
 def test_division_by_three_as_two_fmas_is_the_ieee_quotient(tmp_path):
