@@ -84,7 +84,8 @@ typedef struct HpdParams {
   int32_t force_generic; /* testing only, 0 in production.  bit 0: generic aggregation kernel instead of the specialised
                           * ones, and in top-k the literal libstdc++ heap code (one lane, shared memory) over the whole
                           * row instead of the floor mode / warp-wide heap; bit 1: one warp per row in top-k even for
-                          * small batches.  All variants are bit-identical (tests). */
+                          * small batches; bit 2: rows with ties are streamed by that one warp instead of being handed
+                          * to the second (8 warps per row) launch.  All variants are bit-identical (tests). */
   double det_thr;       /* grouping.py:71,100  (compared in float64) */
   double tag_thr;       /* grouping.py:72,135  (compared in float64) */
   int32_t flip_index[HPD_MAX_KPTS];   /* COCO_FLIP_INDEX (transforms.py:11) */

@@ -17,6 +17,8 @@
 //
 // This file holds the GENERIC kernel (any resize ratios, any number of scales).  It is the
 // correctness anchor; aggregate_nms_x2.cu specialises the standard single-scale x2/x2/x4 case.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 #ifdef HPD_MS_PROFILE
 #include <cstdio>
@@ -58,7 +60,13 @@ struct AggArgs {
   int tags_preflipped;
   int in_vec_ok;   // inputs allow 16-byte loads (aligned bases, strides multiples of 4 elements)
   int in_vec_ok_all;   // ... for every scale
+  int half_in;     // inputs are IEEE halves (HPD_F16); the const float* members then point at __half data
 };
+
+// element i of an input plane (generic kernel: the input type is a run-time flag)
+__device__ __forceinline__ float in_elem(const float* base, size_t i, int half_in) {
+  return half_in ? __half2float(reinterpret_cast<const __half*>(base)[i]) : base[i];
+}
 
 // ---------------------------------------------------------------------------------------------
 // NMS on a (TH+4)x(TW+4) tile already in shared memory (pixels outside the image hold -inf).
@@ -185,8 +193,9 @@ __global__ void __launch_bounds__(kAggThreads) agg_nms_generic_kernel(const AggA
     }
     // flip-averaged low-resolution tile (model.py:90)
     {
-      const float* p = S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc;
-      const float* pf = S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr;
+      const size_t po = (size_t)b * S.lo_sb + (size_t)k * S.lo_sc, pfo = (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc;
+      const float* p = S.lo;
+      const float* pf = S.lo_f;
       const int per = min(nlx, kAggThreads), groups = kAggThreads / per;
       const int rg = tid / per;
       if (rg < groups)
@@ -194,15 +203,16 @@ __global__ void __launch_bounds__(kAggThreads) agg_nms_generic_kernel(const AggA
           const int x = lxa + c;
           for (int r = rg; r < nly; r += groups) {
             const int rowo = (lya + r) * S.lw;
-            float v = p[rowo + x];
-            if (pf) v = __fmul_rn(__fadd_rn(v, pf[rowo + (S.lw - 1 - x)]), 0.5f);
+            float v = in_elem(p, po + rowo + x, a.half_in);
+            if (pf) v = __fmul_rn(__fadd_rn(v, in_elem(pf, pfo + rowo + (S.lw - 1 - x), a.half_in)), 0.5f);
             loT[r * a.LO_C + c] = v;
           }
         }
     }
     {
-      const float* p = S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc;
-      const float* pf = S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr;
+      const size_t po = (size_t)b * S.hi_sb + (size_t)k * S.hi_sc, pfo = (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc;
+      const float* p = S.hi;
+      const float* pf = S.hi_f;
       const int per = min(nhx, kAggThreads), groups = kAggThreads / per;
       const int rg = tid / per;
       if (rg < groups)
@@ -210,8 +220,8 @@ __global__ void __launch_bounds__(kAggThreads) agg_nms_generic_kernel(const AggA
           const int x = hxa + c;
           for (int r = rg; r < nhy; r += groups) {
             const int rowo = (hya + r) * S.hw;
-            float v = p[rowo + x];
-            if (pf) v = __fmul_rn(__fadd_rn(v, pf[rowo + (S.hw - 1 - x)]), 0.5f);
+            float v = in_elem(p, po + rowo + x, a.half_in);
+            if (pf) v = __fmul_rn(__fadd_rn(v, in_elem(pf, pfo + rowo + (S.hw - 1 - x), a.half_in)), 0.5f);
             hiT[r * a.HI_C + c] = v;
           }
         }
@@ -308,12 +318,13 @@ __global__ void __launch_bounds__(kAggThreads) agg_nms_generic_kernel(const AggA
     const int tile_words = a.TG_R * a.TG_C;
     for (int e = 0; e < a.E; ++e) {
       const bool unflip = (e == 1) && !a.tags_preflipped;   // model.py:93: flip(tag_f, W)[:, FLIP]
-      const float* p = (e == 0) ? a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc
-                                : a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc;
+      const float* p = (e == 0) ? a.tag : a.tag_f;
+      const size_t po = (e == 0) ? (size_t)b * a.tag_sb + (size_t)k * a.tag_sc
+                                 : (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc;
       for (int i = tid; i < nty * ntx; i += kAggThreads) {
         const int r = i / ntx, c = i % ntx;
         const int y = tya + r, x = txa + c;
-        loT[e * tile_words + r * a.TG_C + c] = p[(size_t)y * a.tw + (unflip ? a.tw - 1 - x : x)];
+        loT[e * tile_words + r * a.TG_C + c] = in_elem(p, po + (size_t)y * a.tw + (unflip ? a.tw - 1 - x : x), a.half_in);
       }
     }
     __syncthreads();
@@ -433,7 +444,7 @@ int check_map(const HpdMap& m, const char* name, bool required) {
     return HPD_OK;
   }
   if (m.h <= 0 || m.w <= 0) { set_error("%s: bad size %dx%d", name, m.h, m.w); return HPD_EINVAL; }
-  if (m.dtype != HPD_F32) { set_error("%s: unsupported dtype code %d", name, m.dtype); return HPD_EINVAL; }
+  if (m.dtype != HPD_F32 && m.dtype != HPD_F16) { set_error("%s: unsupported dtype code %d", name, m.dtype); return HPD_EINVAL; }
   return HPD_OK;
 }
 
@@ -452,11 +463,20 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
   a.wpr = (p->out_w + 31) / 32;
   for (int k = 0; k < HPD_MAX_KPTS; ++k) a.flip[k] = p->flip_index[k];
   const bool flip = scales[0].hm_lo_f.ptr != nullptr;
+  const int dtype = scales[0].hm_lo.dtype;
+  a.half_in = dtype == HPD_F16;
+  const uintptr_t vec_align = a.half_in ? 8 : 16;    // four elements per vector load
   int LO_R = 1, LO_C = 1, HI_R = 1, HI_C = 1;
   for (int s = 0; s < p->num_scales; ++s) {
     const HpdScaleInputs& in = scales[s];
     int rc;
     if ((rc = check_map(in.hm_lo, "hm_lo", true)) || (rc = check_map(in.hm_hi, "hm_hi", true))) return rc;
+    for (const HpdMap* m : {&in.hm_lo, &in.hm_hi, &in.tag, &in.hm_lo_f, &in.hm_hi_f, &in.tag_f}) {
+      if (m->ptr != nullptr && m->dtype != dtype) {
+        set_error("all maps of a call must share one dtype");
+        return HPD_EINVAL;
+      }
+    }
     if (flip != (in.hm_lo_f.ptr != nullptr) || flip != (in.hm_hi_f.ptr != nullptr)) {
       set_error("flip inputs must be given for all stages and scales or for none");
       return HPD_EINVAL;
@@ -502,7 +522,7 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
   a.tmax = buf->tag_bmax;
   a.tags_preflipped = p->tags_preflipped;
   {
-    auto okp = [](const float* q, long long sb, long long sc_) { return q == nullptr || ((uintptr_t)q % 16 == 0 && sb % 4 == 0 && sc_ % 4 == 0); };
+    auto okp = [vec_align](const float* q, long long sb, long long sc_) { return q == nullptr || ((uintptr_t)q % vec_align == 0 && sb % 4 == 0 && sc_ % 4 == 0); };
     a.in_vec_ok_all = 1;
     for (int s = 0; s < a.n_scales; ++s) {
       const ScaleDev& S = a.sc[s];
@@ -520,21 +540,26 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
                       a.vec_ok;
     if (fast) {
       {
-        auto ok = [](const float* q, long long sb, long long sc_) { return q == nullptr || ((uintptr_t)q % 16 == 0 && sb % 4 == 0 && sc_ % 4 == 0); };
+        auto ok = [vec_align](const float* q, long long sb, long long sc_) { return q == nullptr || ((uintptr_t)q % vec_align == 0 && sb % 4 == 0 && sc_ % 4 == 0); };
         a.in_vec_ok = S.lw % 4 == 0 && ok(S.lo, S.lo_sb, S.lo_sc) && ok(S.hi, S.hi_sb, S.hi_sc) && ok(S.lo_f, S.lof_sb, S.lof_sc) &&
                       ok(S.hi_f, S.hif_sb, S.hif_sc) && ok(a.tag, a.tag_sb, a.tag_sc) && ok(a.tag_f, a.tagf_sb, a.tagf_sc);
       }
       const int NW = a.W >= 512 ? 4 : (a.W >= 256 ? 2 : 1);
       const size_t smem = sizeof(float) * x2::smem_floats(NW, a.E);
       const dim3 grid((a.W + 128 * NW - 1) / (128 * NW), (a.H + x2::RB - 1) / x2::RB, a.B * a.K);
+#define HPD_X2_LAUNCH_T(E_, NW_, T_)                                                                        \
+  do {                                                                                                      \
+    if (int rc_ = ensure_dynamic_smem((const void*)x2::agg_nms_x2_kernel<E_, NW_, T_>, smem, "agg_nms_x2_kernel")) return rc_; \
+    x2::agg_nms_x2_kernel<E_, NW_, T_><<<grid, 32 * NW_, smem, st>>>(a);                                    \
+  } while (0)
 #define HPD_X2_LAUNCH(E_, NW_)                                                                              \
   do {                                                                                                      \
-    if (int rc_ = ensure_dynamic_smem((const void*)x2::agg_nms_x2_kernel<E_, NW_>, smem, "agg_nms_x2_kernel")) return rc_; \
-    x2::agg_nms_x2_kernel<E_, NW_><<<grid, 32 * NW_, smem, st>>>(a);                                        \
+    if (a.half_in) HPD_X2_LAUNCH_T(E_, NW_, __half); else HPD_X2_LAUNCH_T(E_, NW_, float);                  \
   } while (0)
       if (a.E == 1) { if (NW == 4) HPD_X2_LAUNCH(1, 4); else if (NW == 2) HPD_X2_LAUNCH(1, 2); else HPD_X2_LAUNCH(1, 1); }
       else          { if (NW == 4) HPD_X2_LAUNCH(2, 4); else if (NW == 2) HPD_X2_LAUNCH(2, 2); else HPD_X2_LAUNCH(2, 1); }
 #undef HPD_X2_LAUNCH
+#undef HPD_X2_LAUNCH_T
       count_launch();
       return check_launch("agg_nms_x2_kernel");
     }
@@ -542,7 +567,7 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
   // several scales and / or other hi -> output ratios with the HigherHRNet structure (lo -> hi exactly x2,
   // tags exactly x4) -> column-walking multi-scale kernel (aggregate_nms_ms.cuh)
   {
-    bool ok = !p->force_generic && a.n_scales <= 3 && a.in_vec_ok_all && a.th * 4 == a.H && a.tw * 4 == a.W && a.W % 32 == 0 && a.H % 4 == 0 &&
+    bool ok = !p->force_generic && !a.half_in && a.n_scales <= 3 && a.in_vec_ok_all && a.th * 4 == a.H && a.tw * 4 == a.W && a.W % 32 == 0 && a.H % 4 == 0 &&
               a.W >= 256 && a.vec_ok;
     for (int s = 0; ok && s < a.n_scales; ++s) {
       const ScaleDev& S = a.sc[s];

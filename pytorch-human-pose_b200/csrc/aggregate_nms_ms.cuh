@@ -186,8 +186,8 @@ __global__ void __launch_bounds__(32 * NW, 16 / NW) agg_nms_ms_kernel(const AggA
     const float* tg0 = a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc;
     const bool unflip = !a.tags_preflipped;
     const float* tg1 = (E > 1) ? a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc : nullptr;
-    x2::stage_tile<0, TR, tc, NW, false>(sT, tg0, nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
-    if (E > 1) x2::stage_tile<1, TR, tc, NW, false>(sT + TR * tc, nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane);
+    x2::stage_tile<0, TR, tc, NW, false>(sT, tg0, (const float*)nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
+    if (E > 1) x2::stage_tile<1, TR, tc, NW, false>(sT + TR * tc, (const float*)nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane);
     __syncthreads();
     if (active) x2::tags_x4_band<E, RB, TR>(a, sT, tc, txo, X0, y0, b, k, lane);
     __syncthreads();

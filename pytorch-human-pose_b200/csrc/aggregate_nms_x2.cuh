@@ -59,14 +59,31 @@ __device__ __forceinline__ void tap_x2(int o, int I, int& i0, int& i1, float& w0
 // 8 halo columns and for any part right of the map.
 //   MODE 0: dst = p[y][x]      MODE 1: dst = pf[y][mirror ? w-1-x : x]
 //   MODE 2: dst = (p[y][x] + pf[y][w-1-x]) * 0.5   (flip averaging, model.py:90)
+// Input element type: float32 (inference) or IEEE half (the validation-time caller runs the network under fp16
+// autocast, module.py:78).  Halves are widened on load -- exactly -- and everything after is float32 arithmetic.
+template <typename T> struct In;
+template <> struct In<float> {
+  static __device__ __forceinline__ float4 ld4(const float* q) { return __ldg(reinterpret_cast<const float4*>(q)); }
+  static __device__ __forceinline__ float ld1(const float* q) { return __ldg(q); }
+};
+template <> struct In<__half> {
+  static __device__ __forceinline__ float4 ld4(const __half* q) {
+    const uint2 u = __ldg(reinterpret_cast<const uint2*>(q));
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+    return make_float4(a.x, a.y, b.x, b.y);
+  }
+  static __device__ __forceinline__ float ld1(const __half* q) { return __half2float(__ldg(q)); }
+};
+
 template <int MODE>
 __device__ __forceinline__ float stage_combine(float v, float f) {
   return (MODE == 2) ? __fmul_rn(__fadd_rn(v, f), 0.5f) : (MODE == 0 ? v : f);
 }
 
-template <int MODE, int ROWS, int COLS, int NW, bool VEC>
-__device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float* __restrict__ p,
-                                           const float* __restrict__ pf, bool mirror, int yo, int xo, int h, int w,
+template <int MODE, int ROWS, int COLS, int NW, bool VEC, typename T = float>
+__device__ __forceinline__ void stage_tile(float* __restrict__ dst, const T* __restrict__ p,
+                                           const T* __restrict__ pf, bool mirror, int yo, int xo, int h, int w,
                                            int warp, int lane) {
   constexpr int RPB = 2;
   const int xm = w - 1;
@@ -89,13 +106,13 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float*
           f[j][u] = v[j][u];
           if (r < ROWS && q < NV) {
             if (x + 3 <= xm) {
-              if (MODE != 1) v[j][u] = __ldg(reinterpret_cast<const float4*>(p + row + x));
+              if (MODE != 1) v[j][u] = In<T>::ld4(p + row + x);
               if (MODE != 0) {
                 if (mir) {
-                  const float4 t = __ldg(reinterpret_cast<const float4*>(pf + row + (xm - x - 3)));
+                  const float4 t = In<T>::ld4(pf + row + (xm - x - 3));
                   f[j][u] = make_float4(t.w, t.z, t.y, t.x);
                 } else {
-                  f[j][u] = __ldg(reinterpret_cast<const float4*>(pf + row + x));
+                  f[j][u] = In<T>::ld4(pf + row + x);
                 }
               }
             } else {   // right of the map: replicate the last column
@@ -103,8 +120,8 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float*
 #pragma unroll
               for (int c = 0; c < 4; ++c) {
                 const int xc = min(x + c, xm);
-                tv[c] = (MODE != 1) ? __ldg(p + row + xc) : 0.f;
-                tf[c] = (MODE != 0) ? __ldg(pf + row + (mir ? xm - xc : xc)) : 0.f;
+                tv[c] = (MODE != 1) ? In<T>::ld1(p + row + xc) : 0.f;
+                tf[c] = (MODE != 0) ? In<T>::ld1(pf + row + (mir ? xm - xc : xc)) : 0.f;
               }
               v[j][u] = make_float4(tv[0], tv[1], tv[2], tv[3]);
               f[j][u] = make_float4(tf[0], tf[1], tf[2], tf[3]);
@@ -115,8 +132,8 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float*
         if (r < ROWS && lane < 8) {
           const int c = (lane < 4) ? lane : COLS - 8 + lane;
           const int x = clampi(xo + c, 0, xm);
-          if (MODE != 1) hv[j] = __ldg(p + row + x);
-          if (MODE != 0) hf[j] = __ldg(pf + row + (mir ? xm - x : x));
+          if (MODE != 1) hv[j] = In<T>::ld1(p + row + x);
+          if (MODE != 0) hf[j] = In<T>::ld1(pf + row + (mir ? xm - x : x));
         }
       }
 #pragma unroll
@@ -149,8 +166,8 @@ __device__ __forceinline__ void stage_tile(float* __restrict__ dst, const float*
           v[j][u] = 0.f; f[j][u] = 0.f;
           if (r < ROWS && c < COLS) {
             const int x = clampi(xo + c, 0, xm);
-            if (MODE != 1) v[j][u] = __ldg(p + row + x);
-            if (MODE != 0) f[j][u] = __ldg(pf + row + (mir ? xm - x : x));
+            if (MODE != 1) v[j][u] = In<T>::ld1(p + row + x);
+            if (MODE != 0) f[j][u] = In<T>::ld1(pf + row + (mir ? xm - x : x));
           }
         }
       }
@@ -338,7 +355,7 @@ __device__ __forceinline__ void tags_x4_band(const AggArgs& a, const float* __re
   }
 }
 
-template <int E, int NW>
+template <int E, int NW, typename T>
 __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
   extern __shared__ __align__(16) float smem[];
   constexpr int sc = 64 * NW + 8, lc = 32 * NW + 8, tc = 32 * NW + 8;
@@ -369,15 +386,15 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
 
   // ---------------- phase 0a: stage the tag tiles (they alias the half-res tile) ---------------------
   {
-    const float* tg0 = a.tag + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc;
+    const T* tg0 = reinterpret_cast<const T*>(a.tag) + (size_t)b * a.tag_sb + (size_t)k * a.tag_sc;
     const bool unflip = !a.tags_preflipped;   // model.py:93: flip(tag_f, W)[:, FLIP]
-    const float* tg1 = (E > 1) ? a.tag_f + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc : nullptr;
+    const T* tg1 = (E > 1) ? reinterpret_cast<const T*>(a.tag_f) + (size_t)b * a.tagf_sb + (size_t)(unflip ? kf : k) * a.tagf_sc : nullptr;
     if (a.in_vec_ok) {
-      stage_tile<0, TR, tc, NW, true>(sT, tg0, nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
-      if (E > 1) stage_tile<1, TR, tc, NW, true>(sT + TR * tc, nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane);
+      stage_tile<0, TR, tc, NW, true>(sT, tg0, (const T*)nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
+      if (E > 1) stage_tile<1, TR, tc, NW, true>(sT + TR * tc, (const T*)nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane);
     } else {
-      stage_tile<0, TR, tc, NW, false>(sT, tg0, nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
-      if (E > 1) stage_tile<1, TR, tc, NW, false>(sT + TR * tc, nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane);
+      stage_tile<0, TR, tc, NW, false>(sT, tg0, (const T*)nullptr, false, tyo, txo, a.th, a.tw, warp, lane);
+      if (E > 1) stage_tile<1, TR, tc, NW, false>(sT + TR * tc, (const T*)nullptr, tg1, unflip, tyo, txo, a.th, a.tw, warp, lane);
     }
   }
   __syncthreads();
@@ -387,18 +404,18 @@ __global__ void __launch_bounds__(32 * NW) agg_nms_x2_kernel(const AggArgs a) {
 
   // ---------------- phase 1: stage the heatmap inputs -------------------------------------------------
   {
-    const float* lo = S.lo + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc;
-    const float* hi = S.hi + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc;
-    const float* lof = S.lo_f ? S.lo_f + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr;
-    const float* hif = S.hi_f ? S.hi_f + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr;
+    const T* lo = reinterpret_cast<const T*>(S.lo) + (size_t)b * S.lo_sb + (size_t)k * S.lo_sc;
+    const T* hi = reinterpret_cast<const T*>(S.hi) + (size_t)b * S.hi_sb + (size_t)k * S.hi_sc;
+    const T* lof = S.lo_f ? reinterpret_cast<const T*>(S.lo_f) + (size_t)b * S.lof_sb + (size_t)kf * S.lof_sc : nullptr;
+    const T* hif = S.hi_f ? reinterpret_cast<const T*>(S.hi_f) + (size_t)b * S.hif_sb + (size_t)kf * S.hif_sc : nullptr;
 #define HPD_STAGE_ALL(VEC_)                                                                                    \
   do {                                                                                                         \
     if (lof) {                                                                                                 \
       stage_tile<2, LR, lc, NW, VEC_>(sL, lo, lof, true, lyo, lxo, S.lh, S.lw, warp, lane);                    \
       stage_tile<2, SR, sc, NW, VEC_>(sS, hi, hif, true, hyo, hxo, S.hh, S.hw, warp, lane);                    \
     } else {                                                                                                   \
-      stage_tile<0, LR, lc, NW, VEC_>(sL, lo, nullptr, false, lyo, lxo, S.lh, S.lw, warp, lane);               \
-      stage_tile<0, SR, sc, NW, VEC_>(sS, hi, nullptr, false, hyo, hxo, S.hh, S.hw, warp, lane);               \
+      stage_tile<0, LR, lc, NW, VEC_>(sL, lo, (const T*)nullptr, false, lyo, lxo, S.lh, S.lw, warp, lane);               \
+      stage_tile<0, SR, sc, NW, VEC_>(sS, hi, (const T*)nullptr, false, hyo, hxo, S.hh, S.hw, warp, lane);               \
     }                                                                                                          \
   } while (0)
     if (a.in_vec_ok) HPD_STAGE_ALL(true); else HPD_STAGE_ALL(false);

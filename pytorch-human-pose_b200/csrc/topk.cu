@@ -385,9 +385,37 @@ __device__ __forceinline__ void scan_range(Sink& sink, const float* __restrict__
 // pop() removes the largest candidate of the warp.
 struct WordMaxCandidates {
   float t0, t1, t2, t3;   // descending
+  __device__ __forceinline__ void feed(float x) {
+    const float a = fminf(t0, x); t0 = fmaxf(t0, x);
+    const float b = fminf(t1, a); t1 = fmaxf(t1, a);
+    const float c = fminf(t2, b); t2 = fmaxf(t2, b);
+    t3 = fmaxf(t3, c);
+  }
   __device__ __forceinline__ void scan(const float* __restrict__ wm, int w_begin, int w_end, int lane) {
     t0 = t1 = t2 = t3 = -INFINITY;
     constexpr int U = 8;
+    if ((reinterpret_cast<uintptr_t>(wm + w_begin) & 15) == 0) {
+      // 16-byte loads, 8 in flight per lane: 4 KB of word maxima per warp and round trip (the maxima of a
+      // 512x512 plane are 32 KB that the aggregation kernel's map writes have pushed out of L2)
+      for (int base = w_begin; base < w_end; base += 128 * U) {
+        float4 v[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+          const int wd = base + 128 * u + 4 * lane;
+          if (wd + 3 < w_end) {
+            v[u] = *reinterpret_cast<const float4*>(wm + wd);
+          } else {
+            v[u].x = wd < w_end ? wm[wd] : -INFINITY;
+            v[u].y = wd + 1 < w_end ? wm[wd + 1] : -INFINITY;
+            v[u].z = wd + 2 < w_end ? wm[wd + 2] : -INFINITY;
+            v[u].w = -INFINITY;
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) { feed(v[u].x); feed(v[u].y); feed(v[u].z); feed(v[u].w); }
+      }
+      return;
+    }
     for (int base = w_begin; base < w_end; base += 32 * U) {
       float v[U];
 #pragma unroll
@@ -396,12 +424,7 @@ struct WordMaxCandidates {
         v[u] = wd < w_end ? wm[wd] : -INFINITY;
       }
 #pragma unroll
-      for (int u = 0; u < U; ++u) {
-        const float a = fminf(t0, v[u]); t0 = fmaxf(t0, v[u]);
-        const float b = fminf(t1, a);    t1 = fmaxf(t1, a);
-        const float c = fminf(t2, b);    t2 = fmaxf(t2, b);
-        t3 = fmaxf(t3, c);
-      }
+      for (int u = 0; u < U; ++u) feed(v[u]);
     }
   }
   __device__ __forceinline__ float pop(int lane) {
@@ -443,7 +466,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* _
                                                               const float* __restrict__ agg_tags,
                                                               const uint32_t* __restrict__ mask,
                                                               const float* __restrict__ wmax, int rows, int H, int W,
-                                                              int wpr, int E, int M, int force_exact,
+                                                              int wpr, int E, int M, int force_exact, int defer_ties,
                                                               float* __restrict__ scores_k,
                                                               int32_t* __restrict__ idx_k,
                                                               int32_t* __restrict__ coords_k,
@@ -477,6 +500,14 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* _
       fl.init_floor(next_below(floor_v));
       scan_range<SortedSink, true>(fl, hm, mk, wm, W, wpr, 0, H * wpr, 0, lane);
       if (!fl.ambiguous()) { out_v = fl.sv; out_i = fl.si; done = true; }
+      else if (defer_ties) {
+        // Ties among M positive peaks (say, a peak on the image border, which the clamped bilinear taps
+        // duplicate): the order among the equal values is the heap's history, ~M*ln(n/M) insertions.  One warp
+        // would stream them for ~0.3 ms while the other thousand rows are long done, so the row is only marked
+        // here and topk_tied_rows_kernel gives it eight warps.
+        if (lane == 0) idx_k[(size_t)row * M] = -1;
+        return;
+      }
     }
   }
   if (!done && !force_exact) {
@@ -691,6 +722,115 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_split_kernel(const f
   }
 }
 
+// Second launch of the large-batch path: one CTA of kSplitWarps warps per row, rows not marked by topk_kernel
+// leave at once.  The sequential algorithm admits element i iff its value exceeds the M-th largest value before it,
+// so WHICH elements enter can be found in parallel and only the entering elements (~M*ln(n/M), a few hundred)
+// have to go through the exact heap one by one:
+//   1. every warp takes the 16 largest word maxima of its segment of the row;
+//   2. warp s seeds a sorted sink with M placeholders at the M-th largest of the candidates of segments 0..s-1
+//      -- word maxima are values of distinct pixels that lie BEFORE the segment, so this is a lower bound of the
+//      heap top at the segment's start -- and logs every element of its segment that enters the sink: a superset of
+//      what enters the heap there, in index order;
+//   3. warp 0 replays the concatenated logs through the libstdc++ heap (slot i in lane i), filtering against the
+//      live top, and sorts.
+constexpr int kCandPerSeg = 16;
+
+__global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_tied_rows_kernel(const float* __restrict__ agg_hm,
+                                                                         const float* __restrict__ agg_tags,
+                                                                         const uint32_t* __restrict__ mask,
+                                                                         const float* __restrict__ wmax, int H, int W,
+                                                                         int wpr, int E, int M,
+                                                                         float* __restrict__ scores_k,
+                                                                         int32_t* __restrict__ idx_k,
+                                                                         int32_t* __restrict__ coords_k,
+                                                                         float* __restrict__ tags_k) {
+  const int row = blockIdx.x;
+  if (idx_k[(size_t)row * M] != -1) return;
+  __shared__ float s_v[32];
+  __shared__ int s_i[32];
+  __shared__ float s_logv[kSplitWarps][kSegLogCap];
+  __shared__ int s_logi[kSplitWarps][kSegLogCap];
+  __shared__ int s_nlog[kSplitWarps];
+  __shared__ float s_cand[kSplitWarps * kCandPerSeg];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* hm = agg_hm + (size_t)row * H * W;
+  const uint32_t* mk = mask + (size_t)row * H * wpr;
+  const float* wm = wmax + (size_t)row * H * wpr;
+  const int nwords = H * wpr;
+  const int groups = (nwords + 127) / 128;   // segment bounds in whole groups of 128 words
+  const int gb = (groups * warp) / kSplitWarps, ge = (groups * (warp + 1)) / kSplitWarps;
+  const int w_begin = gb * 128, w_end = min(ge * 128, nwords);
+
+  WordMaxCandidates cand;
+  cand.scan(wm, w_begin, w_end, lane);
+  for (int r = 0; r < kCandPerSeg; ++r) {
+    const float x = cand.pop(lane);
+    if (lane == 0) s_cand[warp * kCandPerSeg + r] = x;
+  }
+  __syncthreads();
+  static_assert((kSplitWarps - 1) * kCandPerSeg <= 128, "four candidates per lane below");
+  float floor_s = -INFINITY;
+  if (warp * kCandPerSeg >= M) {
+    cand.t0 = cand.t1 = cand.t2 = cand.t3 = -INFINITY;
+    for (int i = lane; i < warp * kCandPerSeg; i += 32) cand.feed(s_cand[i]);
+    for (int r = 0; r < M; ++r) floor_s = cand.pop(lane);
+  }
+  SortedSink seg;
+  seg.M = M; seg.lane = lane;
+  seg.log_v = s_logv[warp]; seg.log_i = s_logi[warp]; seg.log_cap = kSegLogCap;
+  if (floor_s > -INFINITY) seg.init_floor(floor_s);
+  else seg.init_empty();
+  scan_range(seg, hm, mk, wm, W, wpr, w_begin, w_end, 0, lane);
+  if (lane == 0) s_nlog[warp] = seg.n_log;
+  __syncthreads();
+  if (warp != 0) return;
+
+  bool logs_ok = true;
+  for (int w = 0; w < kSplitWarps; ++w) logs_ok = logs_ok && s_nlog[w] <= kSegLogCap;
+  float out_v = 0.f;
+  int out_i = 0;
+  if (logs_ok) {
+    WarpHeapSink exact;
+    exact.M = M; exact.lane = lane;
+    exact.init(first_element(hm, mk, W, wpr, M, lane));
+    for (int w = 0; w < kSplitWarps; ++w) {
+      const int n = s_nlog[w];
+      for (int i0 = 0; i0 < n; i0 += 32) {
+        const int i = i0 + lane;
+        const float cv = i < n ? s_logv[w][i] : -INFINITY;
+        const int ci = i < n ? s_logi[w][i] : 0;
+        uint32_t pass = __ballot_sync(kFull, i < n && ci >= M && cv > exact.top);
+        while (pass) {
+          const int j = __ffs(pass) - 1;
+          pass &= pass - 1;
+          const float cvj = __shfl_sync(kFull, cv, j);
+          const int cij = __shfl_sync(kFull, ci, j);
+          if (cvj > exact.top) exact.insert(cvj, cij);
+        }
+      }
+    }
+    exact.h.sort(M);
+    out_v = exact.h.v; out_i = exact.h.i;
+  } else {   // a log overflowed: the literal libstdc++ control flow over the whole row
+    HeapSink exact;
+    exact.h = HeapRef{s_v, s_i};
+    exact.M = M; exact.lane = lane;
+    scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
+    __syncwarp();
+    if (lane == 0) sort_heap(exact.h, M);
+    __syncwarp();
+    if (lane < M) { out_v = exact.h.v[lane]; out_i = exact.h.i[lane]; }
+  }
+  if (lane < M) {
+    const size_t o = (size_t)row * M + lane;
+    scores_k[o] = out_v;
+    idx_k[o] = out_i;
+    coords_k[o * 2 + 0] = out_i % W;
+    coords_k[o * 2 + 1] = out_i / W;
+    for (int e = 0; e < E; ++e) tags_k[o * E + e] = agg_tags[((size_t)row * H * W + out_i) * E + e];
+  }
+}
+
 }  // namespace
 
 int launch_topk(const HpdParams* p, const HpdBuffers* buf, cudaStream_t st) {
@@ -707,10 +847,20 @@ int launch_topk(const HpdParams* p, const HpdBuffers* buf, cudaStream_t st) {
     topk_split_kernel<<<rows, kSplitWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->nms_mask, buf->nms_wmax, p->out_h,
                                                          p->out_w, wpr, p->emb, p->max_people, p->force_generic & 1,
                                                          buf->scores_k, buf->idx_k, buf->coords_k, buf->tags_k);
-  else
+  else {
+    // force_generic bit 2 (testing): rows with ties stay in topk_kernel's own one-warp exact stream
+    const bool defer = !(p->force_generic & 1) && !(p->force_generic & 4) && (long long)p->out_h * wpr >= 128 * kSplitWarps;
     topk_kernel<<<(rows + kTopkWarps - 1) / kTopkWarps, kTopkWarps * 32, 0, st>>>(
         buf->agg_hm, buf->agg_tags, buf->nms_mask, buf->nms_wmax, rows, p->out_h, p->out_w, wpr, p->emb, p->max_people,
-        p->force_generic & 1, buf->scores_k, buf->idx_k, buf->coords_k, buf->tags_k);
+        p->force_generic & 1, defer ? 1 : 0, buf->scores_k, buf->idx_k, buf->coords_k, buf->tags_k);
+    if (defer) {
+      count_launch();
+      if (int rc = check_launch("topk_kernel")) return rc;
+      topk_tied_rows_kernel<<<rows, kSplitWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->nms_mask, buf->nms_wmax,
+                                                               p->out_h, p->out_w, wpr, p->emb, p->max_people, buf->scores_k,
+                                                               buf->idx_k, buf->coords_k, buf->tags_k);
+    }
+  }
   count_launch();
   return check_launch("topk_kernel");
 }

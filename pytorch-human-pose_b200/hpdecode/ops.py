@@ -39,11 +39,14 @@ def _require_cuda(t: Tensor, name: str):
         raise _lib.HpdError(f"{name} must be float32 (got {t.dtype})")
 
 
-def _map(t: Optional[Tensor], name: str) -> HpdMap:
+def _map(t: Optional[Tensor], name: str, allow_half: bool = False) -> HpdMap:
     m = HpdMap()
     if t is None:
         return m
-    _require_cuda(t, name)
+    if allow_half and t.is_cuda and t.dtype == torch.float16:
+        m.dtype = _lib.HPD_F16      # network outputs under fp16 autocast (module.py:78): widened inside the kernel
+    else:
+        _require_cuda(t, name)
     if t.dim() != 4:
         raise _lib.HpdError(f"{name} must be [B,K,h,w]")
     if t.stride(3) != 1 or t.stride(2) != t.shape[3]:
@@ -171,7 +174,7 @@ def _scales_struct(scales: Sequence[dict]):
     for i, s in enumerate(scales):
         for name in ("hm_lo", "hm_hi", "tag", "hm_lo_f", "hm_hi_f", "tag_f"):
             t = s.get(name)
-            setattr(arr[i], name, _map(t, name))
+            setattr(arr[i], name, _map(t, name, allow_half=True))
             keep.append(t)
     return arr, keep
 
@@ -269,7 +272,8 @@ def decode_op(hm_lo: Sequence[Tensor], hm_hi: Sequence[Tensor], tag: Sequence[Te
     for name, ts in (("hm_lo", hm_lo), ("hm_hi", hm_hi), ("tag", tag), ("hm_lo_f", hm_lo_f), ("hm_hi_f", hm_hi_f),
                      ("tag_f", tag_f)):
         for t in ts:
-            _require_cuda(t, name)
+            if not (t.is_cuda and t.dtype == torch.float16):
+                _require_cuda(t, name)
     scales = _scales_from_lists(hm_lo, hm_hi, tag, hm_lo_f, hm_hi_f, tag_f)
     B, K = hm_lo[0].shape[:2]
     E = 2 if len(tag_f) > 0 else 1

@@ -59,7 +59,9 @@ def _decode_preaveraged(kpts_heatmaps: List[Tensor], tags_heatmaps: List[Tensor]
     if len(tags_heatmaps) not in (1, 2):
         raise ops._lib.HpdError("1 or 2 tag maps expected")
     dev = _cuda_device(kpts_heatmaps[0])
-    f = lambda t: t.to(dev, torch.float32)
+    half = all(t.dtype == torch.float16 for t in list(kpts_heatmaps) + list(tags_heatmaps))
+    # fp16 network outputs (validation under autocast, module.py:78) go to the kernel as they are
+    f = lambda t: t.to(dev) if half else t.to(dev, torch.float32)
     scale = {"hm_lo": f(kpts_heatmaps[0]), "hm_hi": f(kpts_heatmaps[1]), "tag": f(tags_heatmaps[0])}
     if len(tags_heatmaps) == 2:
         scale["tag_f"] = f(tags_heatmaps[1])

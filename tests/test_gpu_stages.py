@@ -204,6 +204,19 @@ def test_topk_tie_order_matches_oracle(size, levels, peaks, oracle):
     tv, ti = torch.from_numpy(nm).reshape(K, -1).topk(30, dim=1)
     assert np.array_equal(coords_k[..., 1] * size + coords_k[..., 0], ti.numpy())
     assert np.array_equal(_bits(scores_k), _bits(tv.numpy()))
+    # the large-batch path on the same maps: one warp per row with tied rows handed to the second launch
+    # (force_generic 2), and with tied rows streamed inline (6)
+    from hpdecode import ops
+    for force in (2, 6):
+        bufs = ops.DecodeBuffers(1, K, size, size, 2, 30, "cuda:0", torch.from_numpy(hm)[None].cuda(), torch.from_numpy(tg)[None].cuda())
+        p = ops.make_params(1, K, size, size, 2, 30, 0.05, 0.5)
+        ops.run_stage("nms", bufs, p)
+        bufs.idx_k.fill_(-1)                      # stale markers must not confuse the second launch
+        p.force_generic = force
+        ops.run_stage("topk", bufs, p)
+        assert np.array_equal(bufs.idx_k[0].cpu().numpy(), ti.numpy().astype(np.int32)), f"force_generic={force}"
+        assert np.array_equal(_bits(bufs.scores_k[0].cpu().numpy()), _bits(w_scores))
+        assert np.array_equal(_bits(bufs.tags_k[0].cpu().numpy()), _bits(w_tags))
 
 
 @pytest.mark.parametrize("gen,kw,size", [
@@ -221,8 +234,9 @@ def test_topk_fast_path_equals_exact_heap_replay(gen, kw, size):
     outs = []
     # force_generic bits: 1 = exact heap only, 2 = one-warp-per-row kernel instead of the split kernel that
     # small batches get.  0: split + fast, 1: split kernel's sequential exact scan, 2: one warp per row + fast
-    # (with log replay on ties), 3: one warp per row, exact scan
-    for force in (0, 1, 2, 3):
+    # (tied rows go to the second, 8-warps-per-row launch), 6: one warp per row, tied rows streamed inline through
+    # the warp-wide heap, 3: one warp per row, literal libstdc++ scan
+    for force in (0, 1, 2, 6, 3):
         bufs = ops.DecodeBuffers(B, 17, size, size, E, 30, "cuda:0")
         p = ops.make_params(B, 17, size, size, E, 30, 0.05, 0.5)
         ops.run_stage("aggregate_nms", bufs, p, scales=scales)
@@ -275,3 +289,29 @@ def test_multiscale_kernel_is_bit_identical_to_generic(H, W, ratios, tag_scale, 
     lo, hi = blk.amin(dim=(3, 5)), blk.amax(dim=(3, 5))
     slack = 1e-4 * (1 + lo.abs().max())
     assert bool((fast.tag_bmin <= lo + slack).all()) and bool((fast.tag_bmax >= hi - slack).all())
+
+
+@pytest.mark.parametrize("lh,lw,flip,B", [(64, 64, False, 2), (128, 128, True, 1), (48, 80, True, 1), (30, 30, False, 1)])
+def test_half_inputs_equal_float_path_on_upcast_tensors(lh, lw, flip, B, oracle):
+    """fp16 network outputs (autocast, module.py:78).  The halves are widened on load, so every
+    output must equal -- bit for bit -- the float32 path run on the up-cast tensors; specialised and generic
+    kernel, strided channel-slice views included."""
+    s32 = _rand_maps(B, lh, lw, flip, seed=7 + lh)
+    s16 = {k: v.half() for k, v in s32.items()}
+    up = {k: v.float() for k, v in s16.items()}
+    H, W, E = 4 * lh, 4 * lw, 2 if flip else 1
+    want = _run_aggregate([up], H, W, E, False)
+    for force in (False, True):
+        got = _run_aggregate([s16], H, W, E, force)
+        for name in ("agg_hm", "agg_tags", "nms_mask", "hm_wmax"):
+            assert torch.equal(getattr(got, name), getattr(want, name)), f"{name} (generic={force})"
+    both = torch.cat([s16["hm_lo"], s16["tag"]], 1)                       # one 34-channel half tensor, sliced
+    view = dict(s16, hm_lo=both[:, :17], tag=both[:, 17:])
+    got = _run_aggregate([view], H, W, E, False)
+    assert torch.equal(got.agg_hm, want.agg_hm) and torch.equal(got.agg_tags, want.agg_tags)
+    hm_o, tg_o = oracle.aggregate([{k: v[0].cpu().numpy() for k, v in up.items()}], (H, W))
+    assert np.array_equal(_bits(want.agg_hm[0].cpu().numpy()), _bits(hm_o))
+    assert np.array_equal(_bits(want.agg_tags[0].cpu().numpy()), _bits(tg_o))
+    from hpdecode._lib import HpdError
+    with pytest.raises(HpdError):                                          # mixed dtypes are refused
+        _run_aggregate([dict(s16, hm_hi=up["hm_hi"])], H, W, E, False)
