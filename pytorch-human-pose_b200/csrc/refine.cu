@@ -145,11 +145,28 @@ __global__ void __launch_bounds__(32 * HPD_MAX_PEOPLE) adjust_prepare_kernel(con
     const float* m = hm_b + (size_t)lane * H * W;
     const float* t = tg_b + (size_t)lane * H * W * E;
     unsigned long long best = 0ull;
-    for (int j = 0; j < M; ++j) {
-      const int idx = idx_k[bk * M + j];
-      const float v = refine_value(m[idx], t[(size_t)idx * E], (E > 1) ? t[(size_t)idx * E + 1] : 0.f, T0, T1, E);
-      const unsigned long long key = pack_key(v, idx);
-      best = key > best ? key : best;
+    // eight candidates at a time: their index loads, then their heatmap / tag loads, are all in flight together
+    // (one dependent DRAM round trip per candidate made this loop most of the kernel's 30 us)
+    for (int j0 = 0; j0 < M; j0 += 8) {
+      int idx[8];
+      float hv[8], t0[8], t1[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) idx[u] = j0 + u < M ? idx_k[bk * M + j0 + u] : -1;
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        hv[u] = t0[u] = t1[u] = 0.f;
+        if (idx[u] >= 0) {
+          hv[u] = m[idx[u]];
+          t0[u] = t[(size_t)idx[u] * E];
+          if (E > 1) t1[u] = t[(size_t)idx[u] * E + 1];
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        if (idx[u] < 0) continue;
+        const unsigned long long key = pack_key(refine_value(hv[u], t0[u], t1[u], T0, T1, E), idx[u]);
+        best = key > best ? key : best;
+      }
     }
     ws.keys[bk * M + slot] = best;
   }

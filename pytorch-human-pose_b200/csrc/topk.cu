@@ -21,10 +21,21 @@
 // The NMS'd value of a suppressed pixel is x*0 (sign of x): zeros do enter while the top is
 // negative and their indices are part of the bit-exact contract.
 #include "common.cuh"
+#ifdef HPD_TOPK_PROFILE
+#include <cstdio>
+#endif
 
 namespace hpd {
 
 namespace {
+
+// -DHPD_TOPK_PROFILE: the first few tied rows print clock64() per phase of topk_tied_rows_kernel (development aid)
+#ifdef HPD_TOPK_PROFILE
+__device__ int tp_printed = 0;
+#define TP_MARK(i) do { tp[i] = clock64(); } while (0)
+#else
+#define TP_MARK(i)
+#endif
 
 constexpr int kTopkWarps = 4;
 
@@ -125,8 +136,14 @@ struct HeapSink {
 // cycles per insertion than lane 0 editing shared memory.
 struct WarpHeap {
   int lane;
+  unsigned anc;   // ancestors of this lane's node below the root, the node itself included (bit k for node k)
   float v;
   int i;
+  __device__ __forceinline__ void setup(int lane_) {
+    lane = lane_;
+    anc = 0;
+    for (int k = lane_; k >= 1; k = (k - 1) >> 1) anc |= 1u << k;
+  }
   __device__ __forceinline__ void adjust(int hole, int len, float val, int idx) {
     const int lc = min(2 * lane + 1, 31), rc = min(2 * lane + 2, 31);
     const float right = __shfl_sync(kFull, v, rc), left = __shfl_sync(kFull, v, lc);
@@ -168,6 +185,36 @@ struct WarpHeap {
       if (k == j) pj = p[k];
     if (lane == pj) { v = val; i = idx; }
   }
+  // __adjust_heap(first, 0, len, value) -- the call __heap_select and __sort_heap make -- without the level-by-level
+  // walk.  Node k lies on the sift-down path iff every node from k up to (not including) the root was the child
+  // its parent chose, and "was chosen" is one comparison with the sibling: a left child (odd k) is taken when
+  // comp(right, left) or when it has no right sibling (the lone child of an even-length heap), a right child
+  // otherwise.  One ballot collects those bits, one AND against the lane's ancestor mask says whether the lane is
+  // on the path, and since children have larger indices than parents the path in depth order is the path mask in
+  // bit order: __push_heap stops at the deepest path node whose element is not greater than the value (highest
+  // such bit), every path node above it takes its path child's element (one shuffle), that node takes the value.
+  // Same comparisons, same outcome as adjust(0, len, ...); ~3 ballots + 2 shuffles deep instead of a 6-level chain.
+  __device__ __forceinline__ void adjust_root(int len, float val, int idx) {
+    const int sib = (lane & 1) ? lane + 1 : lane - 1;
+    const float sv = __shfl_sync(kFull, v, sib & 31);
+    bool chosen = false;
+    if (lane >= 1 && lane < len) {
+      if (lane & 1) chosen = (lane + 1 < len) ? comp_gt(sv, v) : true;   // left child: comp(right, left), or alone
+      else chosen = !comp_gt(v, sv);                                    // right child: !comp(right, left)
+    }
+    const unsigned sel = __ballot_sync(kFull, chosen);
+    const bool on_path = lane >= 1 && (sel & anc) == anc;
+    const unsigned path = __ballot_sync(kFull, on_path);               // nodes of the path below the root
+    const unsigned above = __ballot_sync(kFull, comp_gt(v, val));      // bit n: comp(first[n], value)
+    const unsigned stop = path & ~above;
+    const int t = stop ? 31 - __clz(stop) : 0;                         // where the value lands
+    int src = lane;
+    if ((lane == 0 || on_path) && lane < t) src = ((path >> (2 * lane + 1)) & 1u) ? 2 * lane + 1 : 2 * lane + 2;
+    const float nv = __shfl_sync(kFull, v, src);
+    const int ni = __shfl_sync(kFull, i, src);
+    v = nv; i = ni;
+    if (lane == t) { v = val; i = idx; }
+  }
   __device__ __forceinline__ void make(int len) {
     if (len < 2) return;
     for (int parent = (len - 2) / 2; parent >= 0; --parent)
@@ -178,7 +225,7 @@ struct WarpHeap {
       const float val = __shfl_sync(kFull, v, last), v0 = __shfl_sync(kFull, v, 0);
       const int idx = __shfl_sync(kFull, i, last), i0 = __shfl_sync(kFull, i, 0);
       if (lane == last) { v = v0; i = i0; }
-      adjust(0, last, val, idx);
+      adjust_root(last, val, idx);
     }
   }
 };
@@ -188,14 +235,14 @@ struct WarpHeapSink {
   int M, lane;
   float top;
   __device__ __forceinline__ void init(float nv) {   // lane < M holds element `lane` of the row
-    h.lane = lane;
+    h.setup(lane);
     h.v = nv;
     h.i = lane;
     h.make(M);
     top = __shfl_sync(kFull, h.v, 0);
   }
   __device__ __forceinline__ void insert(float cv, int idx) {
-    h.adjust(0, M, cv, idx);
+    h.adjust_root(M, cv, idx);
     top = __shfl_sync(kFull, h.v, 0);
   }
   template <bool EQ>
@@ -401,7 +448,11 @@ struct WordMaxCandidates {
         float4 v[U];
 #pragma unroll
         for (int u = 0; u < U; ++u) {
-          const int wd = base + 128 * u + 4 * lane;
+          // which lane reads which 16 bytes of a 128-word chunk rotates from chunk to chunk: maps with regular
+          // structure (a border column, artefacts with a period of a few rows) would otherwise put all their large
+          // maxima into the same few lanes, and a lane keeps only four
+          const int chunk = ((base - w_begin) >> 7) + u;
+          const int wd = base + 128 * u + 4 * ((lane + 5 * chunk) & 31);
           if (wd + 3 < w_end) {
             v[u] = *reinterpret_cast<const float4*>(wm + wd);
           } else {
@@ -455,6 +506,101 @@ __device__ __forceinline__ float first_element(const float* __restrict__ hm, con
   return nv;
 }
 
+// Floor mode's second pass over a whole row: only a few dozen words can hold an element at or above the floor.
+// Streaming them through scan_range costs one DRAM round trip per 32-word group that has one (they are spread
+// all over the row); here their indices are first compacted into a shared-memory list (the word maxima were read
+// a moment ago, so this pass hits the cache) and then expanded eight at a time with all sixteen loads in flight.
+// Returns false -- nothing fed, the sink untouched -- when the list does not fit (the caller then streams the row).
+constexpr int kListCap = 256;
+
+__device__ __forceinline__ bool scan_listed(SortedSink& sink, const float* __restrict__ hm, const uint32_t* __restrict__ mk,
+                                            const float* __restrict__ wm, int W, int wpr, int nwords, int* __restrict__ list_w,
+                                            float* __restrict__ list_m, int lane) {
+  const float top0 = sink.top;
+  int cnt = 0;
+  constexpr int U = 8;
+  for (int base = 0; base < nwords; base += 32 * U) {
+    float v[U];
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const int wd = base + 32 * u + lane;
+      v[u] = wd < nwords ? wm[wd] : -INFINITY;
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) {
+      const bool hit = v[u] >= top0;
+      const unsigned m = __ballot_sync(kFull, hit);
+      if (m) {
+        const int pos = cnt + __popc(m & ((1u << lane) - 1u));
+        if (hit && pos < kListCap) { list_w[pos] = base + 32 * u + lane; list_m[pos] = v[u]; }
+        cnt += __popc(m);
+      }
+    }
+    if (cnt > kListCap) return false;
+  }
+  __syncwarp();
+  if (cnt > 2 * sink.M) {
+    // The floor came from four candidates per lane and can be loose.  The list holds EVERY word maximum at or above
+    // it, the M largest included, so the M-th largest of (a per-lane top-4 of) the list is a better floor; listed
+    // words below it are dropped before anything is loaded.
+    WordMaxCandidates c2;
+    c2.t0 = c2.t1 = c2.t2 = c2.t3 = -INFINITY;
+    for (int i = lane; i < cnt; i += 32) c2.feed(list_m[i]);
+    float f2 = -INFINITY;
+    for (int r = 0; r < sink.M; ++r) f2 = c2.pop(lane);
+    if (f2 > 0.f && next_below(f2) > sink.top) {
+      sink.init_floor(next_below(f2));
+      int kept = 0;
+      for (int base = 0; base < cnt; base += 32) {
+        const int i = base + lane;
+        const int wv = i < cnt ? list_w[i] : 0;
+        const float mv = i < cnt ? list_m[i] : -INFINITY;
+        const bool hit = mv >= sink.top;
+        const unsigned m = __ballot_sync(kFull, hit);
+        __syncwarp();
+        if (hit) {
+          const int pos = kept + __popc(m & ((1u << lane) - 1u));
+          list_w[pos] = wv; list_m[pos] = mv;
+        }
+        kept += __popc(m);
+        __syncwarp();
+      }
+      cnt = kept;
+    }
+  }
+  constexpr int kSlots = 8;
+  for (int b0 = 0; b0 < cnt; b0 += kSlots) {
+    float hv[kSlots];
+    uint32_t mw[kSlots];
+    int w2[kSlots];
+#pragma unroll
+    for (int s2 = 0; s2 < kSlots; ++s2) {
+      w2[s2] = -1; hv[s2] = 0.f; mw[s2] = 0u;
+      if (b0 + s2 < cnt) {
+        w2[s2] = list_w[b0 + s2];
+        const int y = w2[s2] / wpr, x = (w2[s2] - y * wpr) * 32 + lane;
+        if (x < W) hv[s2] = hm[y * W + x];
+        mw[s2] = mk[w2[s2]];
+      }
+    }
+#pragma unroll
+    for (int s2 = 0; s2 < kSlots; ++s2) {
+      if (w2[s2] < 0) break;
+      if (!(list_m[b0 + s2] >= sink.top)) continue;          // the top may have risen meanwhile
+      const int y = w2[s2] / wpr, x0 = (w2[s2] - y * wpr) * 32;
+      const bool keep = (mw[s2] >> lane) & 1u;
+      const float nv = keep ? hv[s2] : __fmul_rn(hv[s2], 0.0f);
+      uint32_t cand = __ballot_sync(kFull, (x0 + lane < W) && nv >= sink.top);
+      while (cand) {
+        const int j = __ffs(cand) - 1;
+        cand &= cand - 1;
+        sink.offer(__shfl_sync(kFull, nv, j), y * W + x0 + j);
+      }
+    }
+  }
+  return true;
+}
+
 template <typename Sink>
 __device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ hm, const uint32_t* __restrict__ mk,
                                          const float* __restrict__ wm, int H, int W, int wpr, int M, int lane) {
@@ -473,6 +619,8 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* _
                                                               float* __restrict__ tags_k) {
   __shared__ float s_v[kTopkWarps][32];
   __shared__ int s_i[kTopkWarps][32];
+  __shared__ int s_list_w[kTopkWarps][kListCap];
+  __shared__ float s_list_m[kTopkWarps][kListCap];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int row = blockIdx.x * kTopkWarps + warp;
   if (row >= rows) return;
@@ -483,6 +631,12 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* _
   float out_v = 0.f;
   int out_i = 0;
   bool done = false;
+#ifdef HPD_TOPK_PROFILE
+  long long tp[8];
+  int path = 0;
+  float floor_dbg = 0.f;
+#endif
+  TP_MARK(0);
   if (!force_exact) {
     // Floor mode: with M word maxima above a positive floor the row holds M positive peaks, the stream can
     // start at that floor instead of at the row's first M elements, and only a few dozen words are ever
@@ -493,12 +647,24 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* _
     cand.scan(wm, 0, H * wpr, lane);
     float floor_v = 0.f;
     for (int i = 0; i < M; ++i) floor_v = cand.pop(lane);
+    TP_MARK(1);
+#ifdef HPD_TOPK_PROFILE
+    floor_dbg = floor_v;
+#endif
     if (floor_v > 0.f) {
       SortedSink fl;
       fl.M = M; fl.lane = lane;
       fl.log_v = nullptr; fl.log_i = nullptr; fl.log_cap = 0;
       fl.init_floor(next_below(floor_v));
-      scan_range<SortedSink, true>(fl, hm, mk, wm, W, wpr, 0, H * wpr, 0, lane);
+      if (!scan_listed(fl, hm, mk, wm, W, wpr, H * wpr, s_list_w[warp], s_list_m[warp], lane)) {
+#ifdef HPD_TOPK_PROFILE
+        path |= 8;
+#endif
+        scan_range<SortedSink, true>(fl, hm, mk, wm, W, wpr, 0, H * wpr, 0, lane);
+      }
+#ifdef HPD_TOPK_PROFILE
+      path |= 1;
+#endif
       if (!fl.ambiguous()) { out_v = fl.sv; out_i = fl.si; done = true; }
       else if (defer_ties) {
         // Ties among M positive peaks (say, a peak on the image border, which the clamped bilinear taps
@@ -519,7 +685,15 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* _
     exact.h.sort(M);
     out_v = exact.h.v; out_i = exact.h.i;
     done = true;
+#ifdef HPD_TOPK_PROFILE
+    path |= 2;
+#endif
   }
+#ifdef HPD_TOPK_PROFILE
+  TP_MARK(2);
+  if (lane == 0 && tp[2] - tp[0] > 60000)
+    printf("slow row %d: floor %g path %d: maxima+pops %lld, rest %lld cycles\n", row, floor_dbg, path, tp[1] - tp[0], tp[2] - tp[1]);
+#endif
   if (!done) {   // force_exact: the literal libstdc++ control flow, lane 0 editing shared memory
     HeapSink exact;
     exact.h = HeapRef{s_v[warp], s_i[warp]};
@@ -726,14 +900,17 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_split_kernel(const f
 // leave at once.  The sequential algorithm admits element i iff its value exceeds the M-th largest value before it,
 // so WHICH elements enter can be found in parallel and only the entering elements (~M*ln(n/M), a few hundred)
 // have to go through the exact heap one by one:
-//   1. every warp takes the 16 largest word maxima of its segment of the row;
-//   2. warp s seeds a sorted sink with M placeholders at the M-th largest of the candidates of segments 0..s-1
-//      -- word maxima are values of distinct pixels that lie BEFORE the segment, so this is a lower bound of the
-//      heap top at the segment's start -- and logs every element of its segment that enters the sink: a superset of
-//      what enters the heap there, in index order;
+//   1. the row is cut into segments that grow geometrically (the entries thin out like M/i, so every segment logs a
+//      few dozen of them);
+//   2. warp s takes the M-th largest word maximum of the words BEFORE its segment -- word maxima are values of
+//      distinct pixels, so this is a lower bound of the heap top at the segment's start -- seeds a sorted sink with M
+//      placeholders at that value and logs every element of its segment that enters the sink: a superset of what
+//      enters the heap there, in index order;
 //   3. warp 0 replays the concatenated logs through the libstdc++ heap (slot i in lane i), filtering against the
 //      live top, and sorts.
-constexpr int kCandPerSeg = 16;
+constexpr int kTiedLogCap = 512;
+// segment s covers [kSegFrac[s], kSegFrac[s+1]) / 256 of the row's words (rounded to whole 32-word groups)
+__constant__ int kSegFrac[kSplitWarps + 1] = {0, 1, 4, 16, 32, 64, 128, 192, 256};
 
 __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_tied_rows_kernel(const float* __restrict__ agg_hm,
                                                                          const float* __restrict__ agg_tags,
@@ -748,70 +925,102 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_tied_rows_kernel(con
   if (idx_k[(size_t)row * M] != -1) return;
   __shared__ float s_v[32];
   __shared__ int s_i[32];
-  __shared__ float s_logv[kSplitWarps][kSegLogCap];
-  __shared__ int s_logi[kSplitWarps][kSegLogCap];
+  __shared__ float s_logv[kSplitWarps][kTiedLogCap];
+  __shared__ int s_logi[kSplitWarps][kTiedLogCap];
   __shared__ int s_nlog[kSplitWarps];
-  __shared__ float s_cand[kSplitWarps * kCandPerSeg];
+  __shared__ int s_ready[kSplitWarps];      // segment s's log is complete (warp 0 replays the logs as they arrive)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (threadIdx.x < kSplitWarps) s_ready[threadIdx.x] = 0;
+  __syncthreads();
   const float* hm = agg_hm + (size_t)row * H * W;
   const uint32_t* mk = mask + (size_t)row * H * wpr;
   const float* wm = wmax + (size_t)row * H * wpr;
   const int nwords = H * wpr;
-  const int groups = (nwords + 127) / 128;   // segment bounds in whole groups of 128 words
-  const int gb = (groups * warp) / kSplitWarps, ge = (groups * (warp + 1)) / kSplitWarps;
-  const int w_begin = gb * 128, w_end = min(ge * 128, nwords);
+  const int ngroups = (nwords + 31) / 32;
+  const int w_begin = min(nwords, 32 * (int)(((long long)ngroups * kSegFrac[warp] + 255) / 256));
+  const int w_end = warp == kSplitWarps - 1 ? nwords : min(nwords, 32 * (int)(((long long)ngroups * kSegFrac[warp + 1] + 255) / 256));
+#ifdef HPD_TOPK_PROFILE
+  long long tp[8];
+  __shared__ long long s_tp[kSplitWarps][4];
+#endif
+  TP_MARK(0);
 
-  WordMaxCandidates cand;
-  cand.scan(wm, w_begin, w_end, lane);
-  for (int r = 0; r < kCandPerSeg; ++r) {
-    const float x = cand.pop(lane);
-    if (lane == 0) s_cand[warp * kCandPerSeg + r] = x;
-  }
-  __syncthreads();
-  static_assert((kSplitWarps - 1) * kCandPerSeg <= 128, "four candidates per lane below");
+  // lower bound of the heap top at the start of this segment: the M-th largest word maximum of the prefix
   float floor_s = -INFINITY;
-  if (warp * kCandPerSeg >= M) {
-    cand.t0 = cand.t1 = cand.t2 = cand.t3 = -INFINITY;
-    for (int i = lane; i < warp * kCandPerSeg; i += 32) cand.feed(s_cand[i]);
+  if (w_begin >= M) {
+    WordMaxCandidates cand;
+    cand.scan(wm, 0, w_begin, lane);
+    TP_MARK(1);
     for (int r = 0; r < M; ++r) floor_s = cand.pop(lane);
+  } else {
+    TP_MARK(1);
   }
   SortedSink seg;
   seg.M = M; seg.lane = lane;
-  seg.log_v = s_logv[warp]; seg.log_i = s_logi[warp]; seg.log_cap = kSegLogCap;
+  seg.log_v = s_logv[warp]; seg.log_i = s_logi[warp]; seg.log_cap = kTiedLogCap;
   if (floor_s > -INFINITY) seg.init_floor(floor_s);
   else seg.init_empty();
+  TP_MARK(2);
   scan_range(seg, hm, mk, wm, W, wpr, w_begin, w_end, 0, lane);
-  if (lane == 0) s_nlog[warp] = seg.n_log;
-  __syncthreads();
+  TP_MARK(3);
+#ifdef HPD_TOPK_PROFILE
+  if (lane == 0) { s_tp[warp][0] = tp[1] - tp[0]; s_tp[warp][1] = tp[2] - tp[1]; s_tp[warp][2] = tp[3] - tp[2]; }
+#endif
+  __syncwarp();
+  if (lane == 0) {
+    s_nlog[warp] = seg.n_log;
+    __threadfence_block();
+    *(volatile int*)&s_ready[warp] = 1;
+  }
   if (warp != 0) return;
+  TP_MARK(4);
 
-  bool logs_ok = true;
-  for (int w = 0; w < kSplitWarps; ++w) logs_ok = logs_ok && s_nlog[w] <= kSegLogCap;
+  // Warp 0 replays segment after segment, each as soon as its warp has finished logging it (the later segments
+  // are still being streamed while the early ones, which hold most of the entries, go through the heap).
   float out_v = 0.f;
   int out_i = 0;
-  if (logs_ok) {
-    WarpHeapSink exact;
-    exact.M = M; exact.lane = lane;
-    exact.init(first_element(hm, mk, W, wpr, M, lane));
-    for (int w = 0; w < kSplitWarps; ++w) {
-      const int n = s_nlog[w];
-      for (int i0 = 0; i0 < n; i0 += 32) {
-        const int i = i0 + lane;
-        const float cv = i < n ? s_logv[w][i] : -INFINITY;
-        const int ci = i < n ? s_logi[w][i] : 0;
-        uint32_t pass = __ballot_sync(kFull, i < n && ci >= M && cv > exact.top);
-        while (pass) {
-          const int j = __ffs(pass) - 1;
-          pass &= pass - 1;
-          const float cvj = __shfl_sync(kFull, cv, j);
-          const int cij = __shfl_sync(kFull, ci, j);
-          if (cvj > exact.top) exact.insert(cvj, cij);
-        }
+  bool logs_ok = true;
+  WarpHeapSink exact;
+  exact.M = M; exact.lane = lane;
+  exact.init(first_element(hm, mk, W, wpr, M, lane));
+  for (int w = 0; w < kSplitWarps && logs_ok; ++w) {
+    while (*(volatile int*)&s_ready[w] == 0) {}
+    __threadfence_block();
+    const int n = *(volatile int*)&s_nlog[w];
+    if (n > kTiedLogCap) { logs_ok = false; break; }
+    for (int i0 = 0; i0 < n; i0 += 32) {
+      const int i = i0 + lane;
+      const float cv = i < n ? s_logv[w][i] : -INFINITY;
+      const int ci = i < n ? s_logi[w][i] : 0;
+      const float top = __shfl_sync(kFull, exact.h.v, 0);
+      uint32_t pass = __ballot_sync(kFull, i < n && ci >= M && cv > top);
+      while (pass) {
+        const int j = __ffs(pass) - 1;
+        pass &= pass - 1;
+        const float cvj = __shfl_sync(kFull, cv, j);
+        const int cij = __shfl_sync(kFull, ci, j);
+        // comp(*i, *first): the element enters iff it is greater than the heap's top right now
+        if (__ballot_sync(kFull, lane == 0 && cvj > exact.h.v)) exact.h.adjust_root(M, cvj, cij);
       }
     }
+  }
+  if (logs_ok) {
+    TP_MARK(5);
     exact.h.sort(M);
+    TP_MARK(6);
+#ifdef HPD_TOPK_PROFILE
+    if (lane == 0 && atomicAdd(&tp_printed, 1) < 80) {
+      int tot = 0;
+      for (int w = 0; w < kSplitWarps; ++w) tot += s_nlog[w];
+      printf("tied row %d: own segment %lld, replay+wait %lld, sort %lld, total %lld cycles; %d log entries\n", row, tp[3] - tp[0],
+             tp[5] - tp[4], tp[6] - tp[5], tp[6] - tp[0], tot);
+    }
+#endif
     out_v = exact.h.v; out_i = exact.h.i;
   } else {   // a log overflowed: the literal libstdc++ control flow over the whole row
+#ifdef HPD_TOPK_PROFILE
+    if (lane == 0) printf("tied row %d: LOG OVERFLOW\n", row);
+#endif
     HeapSink exact;
     exact.h = HeapRef{s_v, s_i};
     exact.M = M; exact.lane = lane;
