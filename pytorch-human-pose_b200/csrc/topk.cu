@@ -351,10 +351,12 @@ struct SortedSink {
 // fetched together instead of one DRAM round trip each.
 // EQ: elements EQUAL to the sink's smallest kept value are fed too (the floor mode needs to see them to
 // know whether its result is free of ties); otherwise only strictly greater ones, as the heap admits.
+// row_max: an upper bound of every word maximum in the range; once the sink's smallest kept value has reached it
+// nothing can enter any more and the scan stops (a channel without positive peaks is done after its first words).
 template <typename Sink, bool EQ = false>
 __device__ __forceinline__ void scan_range(Sink& sink, const float* __restrict__ hm, const uint32_t* __restrict__ mk,
                                            const float* __restrict__ wm, int W, int wpr, int w_begin, int w_end,
-                                           int first_idx, int lane) {
+                                           int first_idx, int lane, float row_max = INFINITY) {
   // words [w_begin, w_end) of the row; pixels with flat index < first_idx are not offered (they are the
   // initial heap of the sequential algorithm)
   const int nwords = w_end;
@@ -369,6 +371,7 @@ __device__ __forceinline__ void scan_range(Sink& sink, const float* __restrict__
       ring[a][u] = wd < nwords ? wm[wd] : -INFINITY;
     }
   for (int base = w_begin; base < nwords; base += 32 * kGroup) {
+    if (!(EQ ? (row_max >= sink.top) : (row_max > sink.top))) return;
     float cur[kGroup];
 #pragma unroll
     for (int u = 0; u < kGroup; ++u) {
@@ -603,9 +606,10 @@ __device__ __forceinline__ bool scan_listed(SortedSink& sink, const float* __res
 
 template <typename Sink>
 __device__ __forceinline__ void scan_row(Sink& sink, const float* __restrict__ hm, const uint32_t* __restrict__ mk,
-                                         const float* __restrict__ wm, int H, int W, int wpr, int M, int lane) {
+                                         const float* __restrict__ wm, int H, int W, int wpr, int M, int lane,
+                                         float row_max = INFINITY) {
   sink.init(first_element(hm, mk, W, wpr, M, lane));
-  scan_range(sink, hm, mk, wm, W, wpr, 0, H * wpr, M, lane);
+  scan_range(sink, hm, mk, wm, W, wpr, 0, H * wpr, M, lane, row_max);
 }
 
 __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* __restrict__ agg_hm,
@@ -631,6 +635,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* _
   float out_v = 0.f;
   int out_i = 0;
   bool done = false;
+  float row_max = INFINITY;
 #ifdef HPD_TOPK_PROFILE
   long long tp[8];
   int path = 0;
@@ -646,7 +651,10 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* _
     WordMaxCandidates cand;
     cand.scan(wm, 0, H * wpr, lane);
     float floor_v = 0.f;
-    for (int i = 0; i < M; ++i) floor_v = cand.pop(lane);
+    for (int i = 0; i < M; ++i) {
+      floor_v = cand.pop(lane);
+      if (i == 0) row_max = floor_v;          // every lane's head is its true maximum: this is the row's largest
+    }
     TP_MARK(1);
 #ifdef HPD_TOPK_PROFILE
     floor_dbg = floor_v;
@@ -681,7 +689,7 @@ __global__ void __launch_bounds__(kTopkWarps * 32, 1) topk_kernel(const float* _
     // row through the exact heap, slot i in lane i
     WarpHeapSink exact;
     exact.M = M; exact.lane = lane;
-    scan_row(exact, hm, mk, wm, H, W, wpr, M, lane);
+    scan_row(exact, hm, mk, wm, H, W, wpr, M, lane, row_max);
     exact.h.sort(M);
     out_v = exact.h.v; out_i = exact.h.i;
     done = true;
@@ -909,8 +917,9 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_split_kernel(const f
 //   3. warp 0 replays the concatenated logs through the libstdc++ heap (slot i in lane i), filtering against the
 //      live top, and sorts.
 constexpr int kTiedLogCap = 512;
-// segment s covers [kSegFrac[s], kSegFrac[s+1]) / 256 of the row's words (rounded to whole 32-word groups)
-__constant__ int kSegFrac[kSplitWarps + 1] = {0, 1, 4, 16, 32, 64, 128, 192, 256};
+// segment s covers [kSegFrac[s], kSegFrac[s+1]) / 1024 of the row's words (rounded up to multiples of 8 words): with
+// ~M/i entries per element every segment logs a few dozen, the first one (which warp 0 both logs and replays) the fewest
+__constant__ int kSegFrac[kSplitWarps + 1] = {0, 1, 4, 16, 64, 128, 256, 512, 1024};
 
 __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_tied_rows_kernel(const float* __restrict__ agg_hm,
                                                                          const float* __restrict__ agg_tags,
@@ -936,9 +945,9 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_tied_rows_kernel(con
   const uint32_t* mk = mask + (size_t)row * H * wpr;
   const float* wm = wmax + (size_t)row * H * wpr;
   const int nwords = H * wpr;
-  const int ngroups = (nwords + 31) / 32;
-  const int w_begin = min(nwords, 32 * (int)(((long long)ngroups * kSegFrac[warp] + 255) / 256));
-  const int w_end = warp == kSplitWarps - 1 ? nwords : min(nwords, 32 * (int)(((long long)ngroups * kSegFrac[warp + 1] + 255) / 256));
+  const int noct = (nwords + 7) / 8;
+  const int w_begin = min(nwords, 8 * (int)(((long long)noct * kSegFrac[warp] + 1023) / 1024));
+  const int w_end = warp == kSplitWarps - 1 ? nwords : min(nwords, 8 * (int)(((long long)noct * kSegFrac[warp + 1] + 1023) / 1024));
 #ifdef HPD_TOPK_PROFILE
   long long tp[8];
   __shared__ long long s_tp[kSplitWarps][4];
@@ -994,13 +1003,19 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_tied_rows_kernel(con
       const int ci = i < n ? s_logi[w][i] : 0;
       const float top = __shfl_sync(kFull, exact.h.v, 0);
       uint32_t pass = __ballot_sync(kFull, i < n && ci >= M && cv > top);
+      // (the next candidate is read -- one broadcast shared-memory load -- while the current one sifts)
+      int j = pass ? __ffs(pass) - 1 : 0;
+      float cvj = s_logv[w][i0 + j];
+      int cij = s_logi[w][i0 + j];
       while (pass) {
-        const int j = __ffs(pass) - 1;
         pass &= pass - 1;
-        const float cvj = __shfl_sync(kFull, cv, j);
-        const int cij = __shfl_sync(kFull, ci, j);
+        const float cur_v = cvj;
+        const int cur_i = cij;
+        j = pass ? __ffs(pass) - 1 : j;
+        cvj = s_logv[w][i0 + j];
+        cij = s_logi[w][i0 + j];
         // comp(*i, *first): the element enters iff it is greater than the heap's top right now
-        if (__ballot_sync(kFull, lane == 0 && cvj > exact.h.v)) exact.h.adjust_root(M, cvj, cij);
+        if (__ballot_sync(kFull, lane == 0 && cur_v > exact.h.v)) exact.h.adjust_root(M, cur_v, cur_i);
       }
     }
   }
