@@ -143,13 +143,17 @@ def host_cores() -> int:
 
 
 def produce_inputs(wl, batch, seed, dev):
-    """One dict of tensors per test scale, on ``dev`` (GPU for the hrnet inputs when there is one)."""
+    """One dict of tensors per test scale, on ``dev`` (GPU for the hrnet inputs when there is one).  hrnet inputs:
+    ONE default-init network (weights from seed 1) for every rank, the images from ``seed`` -- rank r decodes its own
+    images of the same model, like a sharded deployment (rank 0 / N = 1: seed 1 -> images from seed 2, exactly
+    synth_net.network_outputs(B, S, seed=1), the batch tests/test_gpu_workloads.py checks image by image)."""
     import torch
     if wl["inputs"] == "hrnet":
         # BASELINE: heatmaps / tags "produced by random-init HigherHRNet weights on synthetic images"
         from hpdecode import synth_net
-        return [synth_net.network_outputs(batch, scale_input_size(wl["size"], s), flip=True, seed=seed, C=wl["arch"],
-                                          device=dev, chunk=8 if wl["size"] <= 512 else 4) for s in wl["scales"]]
+        return [synth_net.network_outputs(batch, scale_input_size(wl["size"], s), flip=True, seed=1, C=wl["arch"],
+                                          device=dev, chunk=8 if wl["size"] <= 512 else 4, image_seed=seed + 1)
+                for s in wl["scales"]]
     if len(wl["scales"]) != 1:
         raise SystemExit("--inputs netlike|crowd are single-scale generators")
     host = make_inputs(batch, wl["size"], seed=seed, kind=wl["inputs"])
@@ -315,7 +319,7 @@ def run_ours(args):
     else:
         B = wl["batch"]
         total_batch = B * world
-        resident = produce_inputs(wl, B, 1 + rank, dev)
+        resident = produce_inputs(wl, B, 1 + rank + args.seed_offset, dev)
     torch.cuda.synchronize()
     pinned = [{k: v.contiguous().cpu().pin_memory() for k, v in s.items()} for s in resident]
     host = [{k: v[: min(8, B)].numpy() for k, v in s.items()} for s in pinned]
@@ -334,7 +338,9 @@ def run_ours(args):
         G -= 1
     n_groups = NS // G
     ring = torch.empty((NS, B, ROW), device=dev, dtype=torch.uint8)
-    use_graphs = args.graphs == "on" or (args.graphs == "auto" and B < 32)
+    # one graph replay per step instead of eight launches: the host thread stays far ahead of the GPU even when
+    # several ranks (and their NCCL proxy threads) share the box's cores
+    use_graphs = args.graphs != "off"
     pipe = DecodePipeline(dec, depth=NS, records_ring=ring, use_graphs=use_graphs)
     comm = torch.cuda.Stream(device=dev)
     gathered = [torch.empty((world, G * B * ROW), device=dev, dtype=torch.uint8) if (world > 1 and rank == 0) else None
@@ -374,6 +380,8 @@ def run_ours(args):
             pipe.lanes[i]["gate"] = group_done[g]       # the lane's records may be overwritten only after this
 
     def after_tail(ln, res):
+        if args.no_gather:          # diagnosis only: what a step costs without the result gather
+            return
         i = ln["slot"]
         lane_done[i].record()
         state["pending"].append(i)
@@ -490,7 +498,12 @@ def run_ours(args):
         e2e_ok = last
 
     # max over ranks
+    per_rank_ms = [ms_total]
     if world > 1:
+        mine = torch.tensor([ms_total], device=dev, dtype=torch.float64)
+        every = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(every, mine)
+        per_rank_ms = [float(x.item()) for x in every]
         t = torch.tensor([ms_total, e2e_ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total, e2e_ms = t.tolist()
@@ -535,7 +548,10 @@ def run_ours(args):
                     "d2h_bytes_per_step": int(world * B * ROW), "steps": e2e_steps,
                     "host_copy_holds_every_rank": e2e_ok, "pinned_staging": numa_note},
             "gpu_launches": launches, "clocks": clocks, "parity": parity,
+            "per_rank_ms_per_step": [round(x / args.steps, 4) for x in per_rank_ms],
         }
+        if args.no_gather:
+            line["invalid"] = "--no-gather: diagnosis run, the result records were not gathered"
         if world == 1 and not args.no_cpu_baseline:
             cores = min(host_cores(), 32)
             pool = CpuPool(S, cores, host, tag_scale)
@@ -575,8 +591,10 @@ def main():
                     help="hrnet: outputs of a default-init HigherHRNet on seeded random images; netlike / crowd: CPU-generated fields")
     ap.add_argument("--streams", type=int, default=None, help="batches in flight per GPU (1 = strictly sequential)")
     ap.add_argument("--gather-every", type=int, default=None, help="steps per gather collective (default: streams / 2)")
+    ap.add_argument("--seed-offset", type=int, default=0, help="diagnosis: rank r's inputs use seed 1 + r + offset")
+    ap.add_argument("--no-gather", action="store_true", help="diagnosis: skip the gather of the result records (the line is then not a valid bench line)")
     ap.add_argument("--graphs", default="auto", choices=["auto", "on", "off"],
-                    help="CUDA graphs for the per-step launches (auto: per-GPU batch < 32)")
+                    help="CUDA graphs for the per-step launches of the pipelined regions (auto = on)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

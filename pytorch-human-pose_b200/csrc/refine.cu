@@ -223,23 +223,24 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
     // A word matters to a pair if  max(hm) - rint(min distance to the pair's tag)  can reach the pair's
     // running best: the distance is bounded from below through the band's range of the first tag
     // component (tag_bmin / tag_bmax, minus a slack that covers the rounding of the interpolation).
-    float lo = 0.f, hi = 0.f;
-    if (wd < w_end) {
-      const int yw = wd / wpr;
-      const int bi = (yw >> 2) * wpr + (wd - yw * wpr);
-      lo = tlo[bi];
-      hi = thi[bi];
-    }
     auto reach = [&](float hmx, float lo_, float hi_, float Tq) {   // ordered upper bound of the value
       const float slack = 1e-4f * (1.f + fabsf(Tq) + fmaxf(fabsf(lo_), fabsf(hi_)));
       const float dmin = fmaxf(fmaxf(fmaxf(lo_ - Tq, Tq - hi_), 0.f) - slack, 0.f);
       return ordered_u32(__fadd_rn(__fsub_rn(hmx, rintf(dmin)), 0.0f));
     };
     const bool mine = wd < w_end && ((pass_id == 0) ? (hv >= split) : !(hv >= split));
-    // cheap test first: the word's maximum against the smallest running best of all pairs
+    // cheap test first: the word's maximum against the smallest running best of all pairs (most chunks end here,
+    // before the tag bounds -- an integer division and two more loads -- are touched)
     const unsigned thr = __reduce_min_sync(kFull, (unsigned)(best >> 32));
     const unsigned hv_o = ordered_u32(__fadd_rn(hv, 0.0f));
     if (!__any_sync(kFull, mine && hv_o >= thr)) continue;
+    float lo = 0.f, hi = 0.f;
+    if (mine) {
+      const int yw = wd / wpr;
+      const int bi = (yw >> 2) * wpr + (wd - yw * wpr);
+      lo = tlo[bi];
+      hi = thi[bi];
+    }
     const unsigned chunk_max = __reduce_max_sync(kFull, mine ? hv_o : 0u);
     bool viable = false;
     for (int q = 0; q < cnt; ++q) {

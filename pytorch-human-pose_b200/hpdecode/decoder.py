@@ -201,8 +201,7 @@ class DecodePipeline:
         self._next = 0
 
     def _launch(self, ln, bufs, params, scales):
-        for st in self.STAGES:
-            ops.run_stage(st, bufs, params, scales=scales if st == "aggregate_nms" else None)
+        ops.run_decode(scales, bufs, params)      # one C-ABI call: all eight launches on the lane's stream
 
     def submit(self, scales: Sequence[dict], out_hw: Tuple[int, int], tag_scale: int = 0, before_agg=None,
                after_tail=None, inv_affine=None) -> DecodeResult:

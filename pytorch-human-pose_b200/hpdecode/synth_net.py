@@ -114,12 +114,14 @@ class HigherHRNet(nn.Module):
 
 @torch.no_grad()
 def network_outputs(batch: int, size: int = 512, flip: bool = True, seed: int = 0, C: int = 32, device="cuda:0",
-                    chunk: int = 8, num_kpts: int = 17):
+                    chunk: int = 8, num_kpts: int = 17, image_seed=None):
     """One scale dict of CUDA tensors [B,K,h,w] produced by a default-init HigherHRNet-W{C} on seeded
-    N(0,1) images (torch.manual_seed(seed) -> net -> images, the order SURVEY.md 8(d) fixes)."""
+    N(0,1) images (torch.manual_seed(seed) -> net -> images, the order SURVEY.md 8(d) fixes).
+    ``image_seed`` (default seed + 1) seeds the images separately: several ranks then run ONE network
+    (same ``seed``) on different images."""
     torch.manual_seed(seed)
     net = HigherHRNet(num_kpts, C).eval().to(device)
-    g = torch.Generator(device="cpu").manual_seed(seed + 1)
+    g = torch.Generator(device="cpu").manual_seed(seed + 1 if image_seed is None else image_seed)
     out = {k: [] for k in (("hm_lo", "hm_hi", "tag", "hm_lo_f", "hm_hi_f", "tag_f") if flip else ("hm_lo", "hm_hi", "tag"))}
     for b0 in range(0, batch, chunk):
         x = torch.randn(min(chunk, batch - b0), 3, size, size, generator=g).to(device)
