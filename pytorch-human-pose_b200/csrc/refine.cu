@@ -10,10 +10,10 @@
 //   1. adjust_prepare_kernel (one warp per person) adjusts the detected joints, computes the
 //      person score and the person's mean tag T, lists the (person, joint) pairs to refine and
 //      seeds each pair's running best with the joint's top-k candidates;
-//   2. refine_scan_kernel walks the per-word maxima of the raw heatmap (written by the
-//      aggregation kernel, 1/32 of a map) and expands only words whose maximum can still beat
-//      or tie a pair's running best; bests are 64-bit keys (ordered value, ~index) merged with
-//      atomicMax, which implements "largest value, then lowest index" exactly;
+//   2. refine_scan_kernel (one CTA per plane, two sweeps) walks the per-word maxima of the raw
+//      heatmap (written by the aggregation kernel, 1/32 of a map) and expands only words whose
+//      maximum can still beat or tie a pair's running best; bests are 64-bit keys (ordered value,
+//      ~index) merged with atomicMax, which implements "largest value, then lowest index" exactly;
 //   3. refine_apply_kernel turns the winning pixel into the refined joint.
 // All float arithmetic is the reference's float32 sequence (separate mul/add, IEEE sqrt, rint).
 #include "common.cuh"
@@ -174,30 +174,30 @@ __global__ void __launch_bounds__(32 * HPD_MAX_PEOPLE) adjust_prepare_kernel(con
   if (threadIdx.x < K) ws.miss_cnt[(size_t)b * K + threadIdx.x] = do_refine ? s_cnt[threadIdx.x] : 0;
 }
 
-constexpr int kScanWarps = 4;
-constexpr int kScanWordsPerBlock = 1024;
+constexpr int kScanWarps = 16;
 
-// pass 0 expands only words whose raw maximum reaches the joint's M-th top-k score (the words around
-// the strongest peaks), pass 1 the rest.  Running bests are shared through global memory (re-read at
-// every 32-word chunk, published as soon as they improve), so after pass 0 almost every remaining
-// word is pruned by its maximum instead of being climbed flank by flank in index order.
+// One CTA per (image, joint) plane that has pairs to refine.  Two sweeps over the plane's word maxima, the 32-word
+// chunks dealt round-robin to the warps: sweep 0 expands only words whose raw maximum reaches the joint's M-th
+// top-k score (the words around the strongest peaks), sweep 1 the rest.  The running bests live in shared memory
+// (re-read at every chunk, merged with atomicMax as soon as they improve), so after sweep 0 almost every remaining
+// word is pruned by its maximum instead of being climbed flank by flank in index order; the word maxima of
+// sweep 1 are re-read from cache.  (Round 1 ran the sweeps as two launches of 8 CTAs per plane with the bests in
+// global memory: twice the chunk bookkeeping, and an L2 round trip per chunk for the bests.)
 __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const float* __restrict__ agg_hm,
                                                                       const float* __restrict__ agg_tags,
                                                                       const float* __restrict__ hmax,
                                                                       const float* __restrict__ tag_bmin,
                                                                       const float* __restrict__ tag_bmax,
-                                                                      const float* __restrict__ scores_k, int pass_id,
+                                                                      const float* __restrict__ scores_k,
                                                                       int K, int M, int E, int H, int W, int wpr,
                                                                       RefineWs ws) {
-  const int bk = blockIdx.y;
+  const int bk = blockIdx.x;
   const int cnt = ws.miss_cnt[bk];
   if (cnt == 0) return;
+  __shared__ unsigned long long s_best[32];
   const int b = bk / K;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int nwords = H * wpr;
-  const int w_begin = blockIdx.x * kScanWordsPerBlock + warp * (kScanWordsPerBlock / kScanWarps);
-  const int w_end = min(w_begin + kScanWordsPerBlock / kScanWarps, nwords);
-  if (w_begin >= nwords) return;
   const float* m = agg_hm + (size_t)bk * H * W;
   const float* t = agg_tags + (size_t)bk * H * W * E;
   const float* hx = hmax + (size_t)bk * nwords;
@@ -205,7 +205,9 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
   const float* tlo = tag_bmin + (size_t)bk * HB * wpr;
   const float* thi = tag_bmax + (size_t)bk * HB * wpr;
   const float split = scores_k[(size_t)bk * M + M - 1];
-  unsigned long long* gkeys = ws.keys + (size_t)bk * M;
+  unsigned long long* gkeys = s_best;
+  if (threadIdx.x < 32) s_best[threadIdx.x] = threadIdx.x < cnt ? ws.keys[(size_t)bk * M + threadIdx.x] : ~0ull;
+  __syncthreads();
 
   // lane q < cnt tracks listed pair q
   float T0 = 0.f, T1 = 0.f;
@@ -215,11 +217,13 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
     T0 = ws.T[((size_t)b * M + p) * 2 + 0];
     T1 = ws.T[((size_t)b * M + p) * 2 + 1];
   }
+  const int w_end = nwords;
 
-  for (int base = w_begin; base < w_end; base += 32) {
+  for (int pass_id = 0; pass_id < 2; ++pass_id) {
+  for (int base = 32 * warp; base < w_end; base += 32 * kScanWarps) {
     const int wd = base + lane;
     const float hv = wd < w_end ? hx[wd] : -INFINITY;
-    if (lane < cnt) best = __ldcg(gkeys + lane);           // newest bests of all warps working on this joint
+    if (lane < cnt) best = *(volatile unsigned long long*)(gkeys + lane);   // newest bests of all warps of the plane
     // A word matters to a pair if  max(hm) - rint(min distance to the pair's tag)  can reach the pair's
     // running best: the distance is bounded from below through the band's range of the first tag
     // component (tag_bmin / tag_bmax, minus a slack that covers the rounding of the interpolation).
@@ -286,6 +290,9 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
       if (improved && lane < cnt) atomicMax(gkeys + lane, best);
     }
   }
+  __syncthreads();      // every warp has finished this sweep: the next one prunes against the merged bests
+  }
+  if (threadIdx.x < cnt) ws.keys[(size_t)bk * M + threadIdx.x] = s_best[threadIdx.x];
 }
 
 // One block per image.  Phase 1 turns each listed pair's winning pixel into the refined joint (grouping.py:236-249).
@@ -398,14 +405,10 @@ int launch_adjust_refine(const HpdParams* p, const HpdBuffers* buf, void* wsp, s
   int rc = check_launch("adjust_prepare_kernel");
   if (rc) return rc;
   if (p->do_refine) {
-    const int nwords = H * wpr;
-    const dim3 grid((nwords + kScanWordsPerBlock - 1) / kScanWordsPerBlock, B * K);
-    for (int pass_id = 0; pass_id < 2; ++pass_id) {
-      refine_scan_kernel<<<grid, kScanWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->hm_wmax, buf->tag_bmin, buf->tag_bmax, buf->scores_k, pass_id,
-                                                           K, M, E, H, W, wpr, ws);
-      count_launch();
-      if ((rc = check_launch("refine_scan_kernel"))) return rc;
-    }
+    refine_scan_kernel<<<B * K, kScanWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->hm_wmax, buf->tag_bmin, buf->tag_bmax,
+                                                          buf->scores_k, K, M, E, H, W, wpr, ws);
+    count_launch();
+    if ((rc = check_launch("refine_scan_kernel"))) return rc;
   }
   if (!p->do_refine && !buf->records) return HPD_OK;
   if (buf->records && (!buf->flags || (uintptr_t)buf->records % 8 != 0)) {
