@@ -35,7 +35,7 @@ METRIC = "decoded images/s (512x512, HigherHRNet-W32, flip)"
 
 WORKLOADS = {
     # name: arch (HRNet width), size, batch, test scales, inputs, batches in flight
-    "cfg2": dict(arch=32, size=512, batch=64, scales=(1.0,), inputs="hrnet", streams=8, metric=METRIC,
+    "cfg2": dict(arch=32, size=512, batch=64, scales=(1.0,), inputs="hrnet", streams=12, metric=METRIC,
                  text="HigherHRNet-W32 {size}x{size}, batch {batch} per GPU, flip test, single scale (BASELINE configs[2], sharded by image)"),
     "cfg1": dict(arch=32, size=512, batch=1, scales=(1.0,), inputs="hrnet", streams=1,
                  metric="decoded images/s (512x512, HigherHRNet-W32, flip, batch 1)",
@@ -43,7 +43,7 @@ WORKLOADS = {
     "cfg3": dict(arch=48, size=640, batch=32, scales=(0.5, 1.0, 1.5), inputs="hrnet", streams=4,
                  metric="decoded images/s (640x640, HigherHRNet-W48, test scales 0.5/1.0/1.5 + flip)",
                  text="HigherHRNet-W48 {size}x{size}, test scales 0.5/1.0/1.5 + flip, batch {batch} per GPU, scale-aggregated decode (BASELINE configs[3])"),
-    "cfg4": dict(arch=32, size=512, batch=64, scales=(1.0,), inputs="crowd", streams=8,
+    "cfg4": dict(arch=32, size=512, batch=64, scales=(1.0,), inputs="crowd", streams=12,
                  metric="decoded images/s (512x512, planted 30-person crowds, flip)",
                  text="crowded-scene stress: planted 30-person maps {size}x{size}, batch {batch} per GPU, top-k 30, max 30 people (BASELINE configs[4])"),
 }
@@ -333,6 +333,8 @@ def run_ours(args):
     # ring[g*G:(g+1)*G] is gathered on rank 0 by ONE collective on a separate stream (and, in the e2e region, copied to
     # pinned host memory), so no decode stream ever waits for a peer.
     NS = max(1, wl["streams"])
+    if args.streams is None and wl["streams"] > 1 and B < 32:
+        NS = min(32, max(NS, 192 // B))       # small per-GPU batches (strong scaling): more, shorter batches in flight
     G = max(1, NS // 2) if args.gather_every is None else max(1, min(args.gather_every, NS))
     while NS % G:
         G -= 1

@@ -219,10 +219,16 @@ __global__ void __launch_bounds__(kScanWarps * 32) refine_scan_kernel(const floa
   }
   const int w_end = nwords;
 
+  constexpr int kStep = 32 * kScanWarps;
   for (int pass_id = 0; pass_id < 2; ++pass_id) {
-  for (int base = 32 * warp; base < w_end; base += 32 * kScanWarps) {
+  // the word maxima of the next two chunks of this warp are already on their way while one is processed
+  float hv_n1 = (32 * warp + lane < w_end) ? hx[32 * warp + lane] : -INFINITY;
+  float hv_n2 = (32 * warp + kStep + lane < w_end) ? hx[32 * warp + kStep + lane] : -INFINITY;
+  for (int base = 32 * warp; base < w_end; base += kStep) {
     const int wd = base + lane;
-    const float hv = wd < w_end ? hx[wd] : -INFINITY;
+    const float hv = hv_n1;
+    hv_n1 = hv_n2;
+    hv_n2 = (wd + 2 * kStep < w_end) ? hx[wd + 2 * kStep] : -INFINITY;
     if (lane < cnt) best = *(volatile unsigned long long*)(gkeys + lane);   // newest bests of all warps of the plane
     // A word matters to a pair if  max(hm) - rint(min distance to the pair's tag)  can reach the pair's
     // running best: the distance is bounded from below through the band's range of the first tag
