@@ -84,39 +84,64 @@ __device__ __forceinline__ int cv_round_sat(double v) {   // saturate_cast<int>(
   return __double2int_rn(v);
 }
 
+constexpr int kWarpRows = 16;   // output rows per block
+
+// Block = 256 output columns x kWarpRows rows of one image.  The float64 parts of OpenCV's coordinate arithmetic
+// depend on the row alone (X0, Y0) or on the column alone (adelta, bdelta): the first are computed once per block row
+// by 16 threads and shared, the second once per thread, so the per-pixel work is integer arithmetic, four 3-byte taps
+// and three table look-ups (the first version redid eight float64 operations per pixel and was issue-bound at 0.43 TB/s).
 __global__ void __launch_bounds__(256) warp_normalise_kernel(const __grid_constant__ WarpArgs a) {
   __shared__ float lut[3][256];
+  __shared__ int s_x0[kWarpRows], s_y0[kWarpRows];
+  constexpr int AB_SCALE = 1 << kAbBits, ROUND_DELTA = AB_SCALE / (1 << kInterBits) / 2;
+  const int n = blockIdx.z;
+  const WarpImage& I = a.img[n];
+  const int y_first = blockIdx.y * kWarpRows;
   for (int i = threadIdx.x; i < 768; i += blockDim.x) {
     const int c = i >> 8, v = i & 255;
     // to_tensor: uint8 -> float32, div(255); normalize: sub_(mean).div_(std)
     lut[c][v] = __fdiv_rn(__fsub_rn(__fdiv_rn((float)v, 255.0f), a.mean[c]), a.stdv[c]);
   }
+  if (threadIdx.x < kWarpRows) {
+    const double y = (double)(y_first + threadIdx.x);
+    s_x0[threadIdx.x] = cv_round_sat(__dmul_rn(__dadd_rn(__dmul_rn(I.im[1], y), I.im[2]), (double)AB_SCALE)) + ROUND_DELTA;
+    s_y0[threadIdx.x] = cv_round_sat(__dmul_rn(__dadd_rn(__dmul_rn(I.im[4], y), I.im[5]), (double)AB_SCALE)) + ROUND_DELTA;
+  }
   __syncthreads();
-  const int x = blockIdx.x * blockDim.x + threadIdx.x, y = blockIdx.y, n = blockIdx.z;
+  const int x = blockIdx.x * blockDim.x + threadIdx.x;
   if (x >= a.ow) return;
-  const WarpImage& I = a.img[n];
-  constexpr int AB_SCALE = 1 << kAbBits, ROUND_DELTA = AB_SCALE / (1 << kInterBits) / 2;
-  const int X0 = cv_round_sat(__dmul_rn(__dadd_rn(__dmul_rn(I.im[1], (double)y), I.im[2]), (double)AB_SCALE)) + ROUND_DELTA;
-  const int Y0 = cv_round_sat(__dmul_rn(__dadd_rn(__dmul_rn(I.im[4], (double)y), I.im[5]), (double)AB_SCALE)) + ROUND_DELTA;
   const int adelta = cv_round_sat(__dmul_rn(__dmul_rn(I.im[0], (double)x), (double)AB_SCALE));
   const int bdelta = cv_round_sat(__dmul_rn(__dmul_rn(I.im[3], (double)x), (double)AB_SCALE));
-  const int X = (X0 + adelta) >> (kAbBits - kInterBits), Y = (Y0 + bdelta) >> (kAbBits - kInterBits);
-  const int sx = min(max(X >> kInterBits, -32768), 32767), sy = min(max(Y >> kInterBits, -32768), 32767);
-  const int ax = X & 31, ay = Y & 31;
-  // the bilinear table entries (1-fx)(1-fy), fx(1-fy), (1-fx)fy, fx*fy scaled by 2^15 are exact integers
-  const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
-  const bool x0in = sx >= 0 && sx < I.w, x1in = sx + 1 >= 0 && sx + 1 < I.w;
-  const bool y0in = sy >= 0 && sy < I.h, y1in = sy + 1 >= 0 && sy + 1 < I.h;
-  const uint8_t* r0 = I.ptr + (long long)sy * I.stride_row + (long long)sx * 3;
-  const uint8_t* r1 = r0 + I.stride_row;
-  float* o = a.out + (((size_t)n * 3) * a.oh + y) * (size_t)a.ow + x;
+  const size_t plane = (size_t)a.oh * a.ow;
+  float* o = a.out + (size_t)n * 3 * plane + (size_t)y_first * a.ow + x;
+  const int rows = min(kWarpRows, a.oh - y_first);
+#pragma unroll 4
+  for (int r = 0; r < rows; ++r, o += a.ow) {
+    const int X = (s_x0[r] + adelta) >> (kAbBits - kInterBits), Y = (s_y0[r] + bdelta) >> (kAbBits - kInterBits);
+    const int sx = min(max(X >> kInterBits, -32768), 32767), sy = min(max(Y >> kInterBits, -32768), 32767);
+    const int ax = X & 31, ay = Y & 31;
+    // the bilinear table entries (1-fx)(1-fy), fx(1-fy), (1-fx)fy, fx*fy scaled by 2^15 are exact integers
+    const int w00 = (32 - ax) * (32 - ay) * 32, w01 = ax * (32 - ay) * 32, w10 = (32 - ax) * ay * 32, w11 = ax * ay * 32;
+    const bool x0in = sx >= 0 && sx < I.w, x1in = sx + 1 >= 0 && sx + 1 < I.w;
+    const bool y0in = sy >= 0 && sy < I.h, y1in = sy + 1 >= 0 && sy + 1 < I.h;
+    const uint8_t* r0 = I.ptr + (long long)sy * I.stride_row + (long long)sx * 3;
+    const uint8_t* r1 = r0 + I.stride_row;
+    if (x0in && x1in && y0in && y1in) {      // all four taps inside the image (nearly always): no per-tap tests
 #pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int v00 = (y0in && x0in) ? r0[c] : 0, v01 = (y0in && x1in) ? r0[3 + c] : 0;
-    const int v10 = (y1in && x0in) ? r1[c] : 0, v11 = (y1in && x1in) ? r1[3 + c] : 0;
-    const int acc = v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11;
-    const int px = min(max((acc + (1 << (kCoefBits - 1))) >> kCoefBits, 0), 255);
-    o[(size_t)c * a.oh * a.ow] = lut[c][px];
+      for (int c = 0; c < 3; ++c) {
+        const int acc = (int)r0[c] * w00 + (int)r0[3 + c] * w01 + (int)r1[c] * w10 + (int)r1[3 + c] * w11;
+        o[(size_t)c * plane] = lut[c][(acc + (1 << (kCoefBits - 1))) >> kCoefBits];     // weights sum to 2^15: in 0..255
+      }
+    } else {
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        const int v00 = (y0in && x0in) ? r0[c] : 0, v01 = (y0in && x1in) ? r0[3 + c] : 0;
+        const int v10 = (y1in && x0in) ? r1[c] : 0, v11 = (y1in && x1in) ? r1[3 + c] : 0;
+        const int acc = v00 * w00 + v01 * w01 + v10 * w10 + v11 * w11;
+        const int px = min(max((acc + (1 << (kCoefBits - 1))) >> kCoefBits, 0), 255);
+        o[(size_t)c * plane] = lut[c][px];
+      }
+    }
   }
 }
 
@@ -124,7 +149,7 @@ __global__ void __launch_bounds__(256) warp_normalise_kernel(const __grid_consta
 
 int launch_prepare_input(const HpdImage* images, int batch, float* out, int oh, int ow, const float* mean,
                          const float* stdv, cudaStream_t st) {
-  if (!images || !out || !mean || !stdv || batch < 1 || oh < 1 || ow < 1 || oh > 65535) {
+  if (!images || !out || !mean || !stdv || batch < 1 || oh < 1 || ow < 1 || oh > 65535 * kWarpRows) {
     set_error("hpd_prepare_input: bad arguments");
     return HPD_EINVAL;
   }
@@ -155,7 +180,7 @@ int launch_prepare_input(const HpdImage* images, int batch, float* out, int oh, 
     for (int c = 0; c < 3; ++c) { a.mean[c] = mean[c]; a.stdv[c] = stdv[c]; }
     a.out = out + (size_t)b0 * 3 * oh * ow;
     a.oh = oh; a.ow = ow;
-    const dim3 grid((ow + 255) / 256, oh, n);
+    const dim3 grid((ow + 255) / 256, (oh + kWarpRows - 1) / kWarpRows, n);
     warp_normalise_kernel<<<grid, 256, 0, st>>>(a);
     count_launch();
     if (int rc = check_launch("warp_normalise_kernel")) return rc;
