@@ -64,6 +64,36 @@ def test_argument_validation_without_gpu():
     assert L.hpd_workspace_bytes(ctypes.byref(p), ctypes.byref(n)) == 0 and n.value > 0
 
 
+def test_new_entry_points_validate_before_any_launch():
+    """ABI v2 additions: record layout, host geometry and the input kernel reject bad arguments with HPD_EINVAL and
+    a message -- all before a launch, so this runs on a CPU box."""
+    from hpdecode import _lib, ops
+    L = _lib.lib()
+    lay = _lib.HpdRecordLayout()
+    for K, M, E in ((17, 30, 2), (8, 20, 1), (32, 32, 2), (1, 1, 1)):
+        p = ops.make_params(1, K, 256, 256, E, M, 0.05, 0.5)
+        assert L.hpd_record_layout(ctypes.byref(p), ctypes.byref(lay)) == 0
+        assert lay.coco_stride == 3 * K + 1 and lay.off_coco == 0 and lay.off_poses == 8 * M * (3 * K + 1)
+        assert lay.off_person_scores == lay.off_poses + 4 * M * K * (3 + E) and lay.off_n_person == lay.off_person_scores + 4 * M
+        assert lay.off_flags == lay.off_n_person + 4 and lay.row_bytes % 8 == 0 and lay.row_bytes >= lay.off_flags + 4
+    p = ops.make_params(1, 40, 256, 256, 1, 30, 0.05, 0.5)
+    assert L.hpd_record_layout(ctypes.byref(p), ctypes.byref(lay)) == 1 and b"out of range" in L.hpd_last_error_string()
+    size, center, scale = (ctypes.c_int32 * 2)(), (ctypes.c_int32 * 2)(), (ctypes.c_double * 2)()
+    assert L.hpd_multi_scale_size(0, 640, 512, 1.0, 1.0, size, center, scale) == 1
+    assert L.hpd_multi_scale_size(480, 640, 512, 1.0, 0.0, size, center, scale) == 1
+    assert L.hpd_get_affine_transform(None, scale, size, 0, (ctypes.c_double * 6)()) == 1
+    img = (_lib.HpdImage * 1)()
+    mean, std = (ctypes.c_float * 3)(0.5, 0.5, 0.5), (ctypes.c_float * 3)(0.2, 0.2, 0.2)
+    assert L.hpd_prepare_input(img, 1, None, 64, 64, mean, std, None) == 1                     # no output buffer
+    assert L.hpd_prepare_input(img, 1, ctypes.c_void_p(8), 64, 64, mean, std, None) == 1       # image 0 has no pointer
+    assert b"image 0" in L.hpd_last_error_string()
+    img[0].ptr, img[0].h, img[0].w, img[0].stride_row = 8, 10, 10, 20                          # stride < 3 * w
+    assert L.hpd_prepare_input(img, 1, ctypes.c_void_p(8), 64, 64, mean, std, None) == 1
+    m = _lib.HpdMap()
+    m.ptr, m.h, m.w, m.dtype = 8, 4, 4, 7                                                      # unknown dtype code
+    assert L.hpd_resize_bilinear(ctypes.byref(m), 1, 1, ctypes.c_void_p(8), 8, 8, None) == 1
+
+
 def test_product_fails_loudly_without_cuda():
     import torch
     if torch.cuda.is_available():
