@@ -86,6 +86,10 @@ typedef struct HpdParams {
                           * row instead of the floor mode / warp-wide heap; bit 1: one warp per row in top-k even for
                           * small batches; bit 2: rows with ties are streamed by that one warp instead of being handed
                           * to the second (8 warps per row) launch.  All variants are bit-identical (tests). */
+  int32_t batches_in_flight; /* hint, 0 or 1 = unknown / latency matters: small batches (<= 512 rows) give every top-k row eight
+                          * warps; >= 8: the caller keeps that many batches in flight (DecodePipeline), so the row gets one
+                          * warp and the batches overlap instead (+5 % throughput at 8-16 images per batch).  Same results. */
+  int32_t reserved_;
   double det_thr;       /* grouping.py:71,100  (compared in float64) */
   double tag_thr;       /* grouping.py:72,135  (compared in float64) */
   int32_t flip_index[HPD_MAX_KPTS];   /* COCO_FLIP_INDEX (transforms.py:11) */

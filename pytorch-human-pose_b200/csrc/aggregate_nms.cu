@@ -535,7 +535,7 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
   // standard single-scale x2/x2/x4 layout -> specialised kernel (aggregate_nms_x2.cuh)
   {
     const ScaleDev& S = a.sc[0];
-    const bool fast = !p->force_generic && a.n_scales == 1 && S.hh == 2 * S.lh && S.hw == 2 * S.lw && a.H == 2 * S.hh &&
+    const bool fast = !(p->force_generic & 1) && a.n_scales == 1 && S.hh == 2 * S.lh && S.hw == 2 * S.lw && a.H == 2 * S.hh &&
                       a.W == 2 * S.hw && a.th == S.lh && a.tw == S.lw && a.W % 32 == 0 && S.lh >= 2 && S.lw >= 2 &&
                       a.vec_ok;
     if (fast) {
@@ -567,7 +567,7 @@ int launch_aggregate_nms(const HpdParams* p, const HpdScaleInputs* scales, const
   // several scales and / or other hi -> output ratios with the HigherHRNet structure (lo -> hi exactly x2,
   // tags exactly x4) -> column-walking multi-scale kernel (aggregate_nms_ms.cuh)
   {
-    bool ok = !p->force_generic && !a.half_in && a.n_scales <= 3 && a.in_vec_ok_all && a.th * 4 == a.H && a.tw * 4 == a.W && a.W % 32 == 0 && a.H % 4 == 0 &&
+    bool ok = !(p->force_generic & 1) && !a.half_in && a.n_scales <= 3 && a.in_vec_ok_all && a.th * 4 == a.H && a.tw * 4 == a.W && a.W % 32 == 0 && a.H % 4 == 0 &&
               a.W >= 256 && a.vec_ok;
     for (int s = 0; ok && s < a.n_scales; ++s) {
       const ScaleDev& S = a.sc[s];

@@ -1066,7 +1066,8 @@ int launch_topk(const HpdParams* p, const HpdBuffers* buf, cudaStream_t st) {
   const int rows = p->batch * p->num_kpts;
   const int wpr = (p->out_w + 31) / 32;
   // small batches: kSplitWarps warps per row cut the per-row latency; large ones fill the GPU with one warp per row
-  const bool split = rows <= 512 && (long long)p->out_h * wpr >= 128 * kSplitWarps && !(p->force_generic & 2);
+  const bool split = rows <= 512 && (long long)p->out_h * wpr >= 128 * kSplitWarps && !(p->force_generic & 2) &&
+                     p->batches_in_flight < 8;
   if (split)
     topk_split_kernel<<<rows, kSplitWarps * 32, 0, st>>>(buf->agg_hm, buf->agg_tags, buf->nms_mask, buf->nms_wmax, p->out_h,
                                                          p->out_w, wpr, p->emb, p->max_people, p->force_generic & 1,

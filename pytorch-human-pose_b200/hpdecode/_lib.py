@@ -38,6 +38,7 @@ class HpdParams(ctypes.Structure):
                 ("out_w", ctypes.c_int32), ("emb", ctypes.c_int32), ("max_people", ctypes.c_int32),
                 ("num_scales", ctypes.c_int32), ("tag_scale", ctypes.c_int32), ("do_adjust", ctypes.c_int32),
                 ("do_refine", ctypes.c_int32), ("tags_preflipped", ctypes.c_int32), ("force_generic", ctypes.c_int32),
+                ("batches_in_flight", ctypes.c_int32), ("reserved_", ctypes.c_int32),
                 ("det_thr", ctypes.c_double), ("tag_thr", ctypes.c_double),
                 ("flip_index", ctypes.c_int32 * HPD_MAX_KPTS), ("joints_order", ctypes.c_int32 * HPD_MAX_KPTS)]
 

@@ -219,6 +219,7 @@ class DecodePipeline:
             bufs.records = self.records_ring[ln["slot"]]
         params = ops.make_params(B, d.num_kpts, H, W, E, d.max_num_people, d.det_thr, d.tag_thr, d.adjust, d.refine,
                                  len(scales), tag_scale)
+        params.batches_in_flight = self.depth       # >= 8: small batches take the throughput-oriented top-k launch
         cur = torch.cuda.current_stream(d.device)
         st = ln["stream"]
         if inv_affine is not None or bufs.inv_affine is not None:
