@@ -7,7 +7,7 @@ out bit-identical to cv2.getAffineTransform); ``resize_align_multi_scale`` + ToT
 arithmetic, so the tensor handed to the network is bit-identical to the reference's.
 """
 import ctypes
-from typing import List, Sequence, Tuple
+from typing import Sequence, Tuple
 
 import numpy as np
 import torch

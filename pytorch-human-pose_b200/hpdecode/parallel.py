@@ -2,7 +2,7 @@
 communication is a gather of the fixed-size packed pose lists to rank 0 (NCCL on CUDA tensors;
 the same code runs over gloo on CPU tensors in the tests).  No collective touches the hot path
 (SURVEY.md 8(e))."""
-from typing import List, Optional, Tuple
+from typing import Optional, Tuple
 
 import torch
 import torch.distributed as dist

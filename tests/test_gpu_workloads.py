@@ -51,7 +51,7 @@ def test_bench_workload_through_the_pipeline(oracle):
     """The same workload through DecodePipeline (what bench.py's timed region runs): 3 submits on 2 lanes,
     the packed rows of the last submit checked against the oracle for 8 images."""
     from hpdecode import BottomUpDecoder, synth_net
-    from hpdecode.decoder import DecodePipeline, DecodeResult
+    from hpdecode.decoder import DecodePipeline
     B, S = 64, 512
     scale = synth_net.network_outputs(B, S, flip=True, seed=1, C=32, device="cuda:0")
     dec = BottomUpDecoder(17, 30, 0.05, 0.5, "cuda:0")

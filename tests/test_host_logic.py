@@ -1,10 +1,8 @@
 """CPU suite: host-side logic -- synthetic generators, result packing, sharding and the
 world_size-2 gather over gloo (the N>1 path of bench.py without GPUs)."""
 import os
-import sys
 
 import numpy as np
-import pytest
 import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp

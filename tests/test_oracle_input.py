@@ -80,7 +80,6 @@ def test_library_host_geometry_many_sizes_against_oracle():
 def test_input_oracle_against_live_reference_cv2_and_torchvision():
     sys.path.insert(0, REF)
     import cv2
-    import torch
     import torchvision.transforms as T
     from src.base.transforms.utils import affine_transform, get_affine_transform, get_multi_scale_size, resize_align_multi_scale
     tf = T.Compose([T.ToTensor(), T.Normalize(mean=[0.485, 0.456, 0.406], std=[0.229, 0.224, 0.225])])

@@ -1,4 +1,4 @@
-import sys, time
+import sys
 sys.path.insert(0,'pytorch-human-pose_b200'); sys.path.insert(0,'.')
 import torch, numpy as np
 from hpdecode import synth_net, synth, ops

@@ -4,7 +4,7 @@ import sys, os
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "pytorch-human-pose_b200"))
 import torch
-from hpdecode import BottomUpDecoder, synth, ops
+from hpdecode import BottomUpDecoder, synth
 
 dev = lambda sc: [{k: torch.from_numpy(v).cuda() for k, v in s.items()} for s in sc]
 dec = BottomUpDecoder(17, 30, 0.05, 0.5, "cuda:0")
