@@ -354,7 +354,7 @@ def run_ours(args):
         os.sched_setaffinity(0, old_affinity)
     group_done = [torch.cuda.Event() for _ in range(n_groups)]
     lane_done = [torch.cuda.Event() for _ in range(NS)]
-    state = {"to_host": False, "pending": []}
+    state = {"to_host": False, "pending": [], "expected_records": None}
     main = torch.cuda.current_stream(dev)
     bufs = dec.buffers(B, S, S, E, slot=NS)            # a buffer set of its own for the sequential stage timing
 
@@ -432,6 +432,7 @@ def run_ours(args):
                 np.array_equal(np.asarray(gj, np.float32).view(np.uint32), ref["grouped_joints"].view(np.uint32)) and \
                 np.array_equal(np.asarray(ps, np.float32).view(np.uint32), ref["person_scores"].view(np.uint32))
         info = {"checked": n_check * world, "ok": bool(ok), "against": "oracle/hpd_oracle.cpp (grouped joints + person scores, bit-exact)"}
+        state["expected_records"] = res.records.clone()      # what every pipelined step must reproduce for this batch
         if world > 1:
             digest = torch.frombuffer(bytearray(hashlib.sha256(rows.tobytes()).digest()), dtype=torch.uint8).to(dev)
             digests = [torch.empty_like(digest) for _ in range(world)]
@@ -476,6 +477,14 @@ def run_ours(args):
     l0 = ops.launches_total()
     ms_total = run_steps(args.steps, value_step)
     launches = ops.launches_total() - l0
+    # the timed steps really decoded: every lane's records equal the ones checked against the oracle above
+    lanes_used = min(NS, args.steps)
+    parity["pipelined_records_identical"] = bool(all(torch.equal(ring[i], state["expected_records"]) for i in range(lanes_used)))
+    if world > 1:
+        flag = torch.tensor([int(parity["pipelined_records_identical"])], device=dev)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+        parity["pipelined_records_identical"] = bool(flag.item())
+    parity["ok"] = parity["ok"] and parity["pipelined_records_identical"]
 
     # ---- e2e: host buffers, H2D of the inputs and D2H of the result records inside the timed region ---------
     state["to_host"] = True

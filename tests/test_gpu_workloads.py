@@ -133,3 +133,31 @@ def test_pipeline_inputs_may_be_dropped_after_submit():
     got = results[-1].to_numpy()
     for (wg, wp), (gg, gp) in zip(want, got):
         assert np.array_equal(_bits(wg), _bits(gg)) and np.array_equal(_bits(wp), _bits(gp))
+
+
+def test_pipeline_with_cuda_graphs_and_records_ring(oracle):
+    """What bench.py's timed region runs: DecodePipeline with one CUDA-graph replay per submit and the lanes' result
+    records aimed at a ring.  Static inputs (graphs bake the pointers in), 7 submits over 3 lanes, small batch with
+    ``batches_in_flight`` >= 8 semantics exercised separately by the top-k tests."""
+    from hpdecode import BottomUpDecoder, ops, synth
+    from hpdecode.decoder import DecodePipeline, Records
+    dec = BottomUpDecoder(17, 30, 0.05, 0.5, "cuda:0")
+    host = synth.crowd(4, 256, persons=11, flip=True, seed=31)
+    dev = [{k: torch.from_numpy(v).cuda() for k, v in s.items()} for s in host]
+    want = dec.decode(dev, (256, 256), slot=9).records.clone()
+    row = ops.record_layout(17, 30, 2).row_bytes
+    ring = torch.zeros((3, 4, row), device="cuda", dtype=torch.uint8)
+    pipe = DecodePipeline(dec, depth=3, records_ring=ring, use_graphs=True)
+    for _ in range(7):
+        pipe.submit(dev, (256, 256))
+    pipe.drain()
+    torch.cuda.synchronize()
+    assert pipe.graph_replays == 7
+    for lane in range(3):
+        assert torch.equal(ring[lane], want)
+    rec = Records(ring[1].cpu().numpy(), 30, 17, 2)
+    for b in range(4):
+        hm_o, tg_o = oracle.aggregate(synth.image_slice(host, b), (256, 256))
+        ref = oracle.parse(hm_o, tg_o, 30, 0.05, 0.5)
+        gj, ps = rec.image(b)
+        assert np.array_equal(_bits(gj), _bits(ref["grouped_joints"])) and np.array_equal(_bits(ps), _bits(ref["person_scores"]))
