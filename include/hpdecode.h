@@ -204,6 +204,12 @@ HPD_EXPORT int hpd_multi_scale_size(int img_h, int img_w, int input_size, double
 HPD_EXPORT int hpd_get_affine_transform(const double center_xy[2], const double scale_wh[2], const int32_t output_size_wh[2],
                                         int inverse, double m_out[6]);
 
+/* Both of the above for n images in one call (the batched evaluation loop): per image i the resized size, center, scale,
+ * the forward matrix (for hpd_prepare_input) and the inverse one (for HpdBuffers.inv_affine). */
+HPD_EXPORT int hpd_prepare_geometry(int n, const int32_t* img_h, const int32_t* img_w, int input_size, double current_scale,
+                                    double min_scale, int32_t* size_resized_wh /*[n][2]*/, int32_t* center_xy /*[n][2]*/,
+                                    double* scale_wh /*[n][2]*/, double* m_forward /*[n][6]*/, double* m_inverse /*[n][6]*/);
+
 /* resize_align_multi_scale's cv2.warpAffine (INTER_LINEAR, BORDER_CONSTANT 0; base/transforms/utils.py:96) followed by
  * T.ToTensor + T.Normalize (model.py:45-50): images_host[b] (uint8 HWC on the device, descriptors on the host) ->
  * out [batch,3,out_h,out_w] float32.  The warp replays OpenCV's fixed-point arithmetic (10-bit coordinates, 5-bit

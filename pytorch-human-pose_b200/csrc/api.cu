@@ -165,6 +165,24 @@ int hpd_get_affine_transform(const double center_xy[2], const double scale_wh[2]
   return affine_transform_matrix(center_xy, scale_wh, output_size_wh, inverse, m_out);
 }
 
+int hpd_prepare_geometry(int n, const int32_t* img_h, const int32_t* img_w, int input_size, double current_scale,
+                         double min_scale, int32_t* size_resized_wh, int32_t* center_xy, double* scale_wh, double* m_forward,
+                         double* m_inverse) {
+  if (n < 1 || !img_h || !img_w || !size_resized_wh || !center_xy || !scale_wh || !m_forward || !m_inverse) {
+    set_error("hpd_prepare_geometry: bad arguments");
+    return HPD_EINVAL;
+  }
+  for (int i = 0; i < n; ++i) {
+    int rc = multi_scale_size(img_h[i], img_w[i], input_size, current_scale, min_scale, size_resized_wh + 2 * i,
+                              center_xy + 2 * i, scale_wh + 2 * i);
+    if (rc) return rc;
+    const double c[2] = {(double)center_xy[2 * i], (double)center_xy[2 * i + 1]};
+    if ((rc = affine_transform_matrix(c, scale_wh + 2 * i, size_resized_wh + 2 * i, 0, m_forward + 6 * i))) return rc;
+    if ((rc = affine_transform_matrix(c, scale_wh + 2 * i, size_resized_wh + 2 * i, 1, m_inverse + 6 * i))) return rc;
+  }
+  return HPD_OK;
+}
+
 int hpd_prepare_input(const HpdImage* images_host, int batch, float* out, int out_h, int out_w, const float mean[3],
                       const float std_[3], void* stream) {
   g_launches = 0;

@@ -19,7 +19,7 @@ LIB_PATH = os.path.join(_HERE, "libhpdecode.so")
 EXPORTS = (
     "hpd_abi_version", "hpd_last_error_string", "hpd_workspace_bytes", "hpd_aggregate_nms", "hpd_nms",
     "hpd_topk", "hpd_group", "hpd_adjust_refine", "hpd_decode", "hpd_last_launch_count", "hpd_resize_bilinear",
-    "hpd_record_layout", "hpd_multi_scale_size", "hpd_get_affine_transform", "hpd_prepare_input",
+    "hpd_record_layout", "hpd_multi_scale_size", "hpd_get_affine_transform", "hpd_prepare_input", "hpd_prepare_geometry",
 )
 
 
@@ -95,6 +95,8 @@ def lib():
     L.hpd_multi_scale_size.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double, ctypes.c_double, I32P,
                                        I32P, F64P]
     L.hpd_get_affine_transform.argtypes = [F64P, F64P, I32P, ctypes.c_int, F64P]
+    L.hpd_prepare_geometry.argtypes = [ctypes.c_int, I32P, I32P, ctypes.c_int, ctypes.c_double, ctypes.c_double, I32P, I32P, F64P,
+                                       F64P, F64P]
     L.hpd_prepare_input.argtypes = [ctypes.POINTER(HpdImage), ctypes.c_int, V, ctypes.c_int, ctypes.c_int, F32P, F32P, V]
     for n in EXPORTS:
         if n not in ("hpd_last_error_string",):

@@ -42,7 +42,6 @@ def evaluate_dataset_batched(model, dataset, batch_size: int = 32, limit: Option
     ``images_filepaths`` and ``load_image(idx)`` (datasets/coco.py).  Images are loaded ``batch_size`` at a time,
     grouped by resized size inside ``model.predict_batch``-like steps, decoded on the device, and the COCO dicts
     are read from the records' COCO section -- no per-person host arithmetic."""
-    import numpy as np
     from . import geometry
     n = len(dataset) if limit is None else min(limit, len(dataset))
     results: List[dict] = []
@@ -55,11 +54,9 @@ def evaluate_dataset_batched(model, dataset, batch_size: int = 32, limit: Option
         groups = geometry.group_by_resized_size([im.shape[:2] for im in images], model.input_size, 1.0, min_scale)
         for size, members in groups.items():
             imgs = [images[j] for j in members]
-            x, centers, scales = geometry.prepare_input(imgs, model.input_size, model.device, 1.0, min_scale)
+            x, _, _, minv = geometry.prepare_input(imgs, model.input_size, model.device, 1.0, min_scale, return_inverse=True)
             extra = [geometry.prepare_input(imgs, model.input_size, model.device, s, min_scale)[0]
                      for s in model.test_scales if s != 1.0]
-            minv = np.stack([geometry.get_affine_transform(c, s, 0, size, inverse=True).ravel()
-                             for c, s in zip(centers, scales)])
             rec = model.forward_decode(x, inv_affine=minv, extra_scales=extra).host()
             for b, j in enumerate(members):
                 per_image[j] = rec.coco_records(b, ids[j])

@@ -40,32 +40,49 @@ def get_affine_transform(center, scale, rot: float, output_size, shift=(0, 0), i
     return np.array(m[:], np.float64).reshape(2, 3)
 
 
+def prepare_geometry(shapes_hw: Sequence[Tuple[int, int]], input_size: int, current_scale: float = 1, min_scale: float = 1):
+    """get_multi_scale_size + both affine matrices for n images in ONE library call:
+    (sizes int32 [n,2] (w,h), centers int32 [n,2], scales float64 [n,2], forward float64 [n,6], inverse float64 [n,6])."""
+    n = len(shapes_hw)
+    hs = np.ascontiguousarray([s[0] for s in shapes_hw], np.int32)
+    ws = np.ascontiguousarray([s[1] for s in shapes_hw], np.int32)
+    sizes, centers = np.empty((n, 2), np.int32), np.empty((n, 2), np.int32)
+    scales, fwd, inv = np.empty((n, 2), np.float64), np.empty((n, 6), np.float64), np.empty((n, 6), np.float64)
+    i32 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+    f64 = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))
+    _lib.check(_lib.lib().hpd_prepare_geometry(n, i32(hs), i32(ws), int(input_size), float(current_scale), float(min_scale),
+                                               i32(sizes), i32(centers), f64(scales), f64(fwd), f64(inv)), "hpd_prepare_geometry")
+    return sizes, centers, scales, fwd, inv
+
+
 def prepare_input(images: Sequence, input_size: int, device, current_scale: float = 1, min_scale: float = 1,
-                  mean=MEAN, std=STD):
+                  mean=MEAN, std=STD, return_inverse: bool = False):
     """Batched ``InferenceKeypointsModel.prepare_input`` (model.py:70-76) on the device.
 
     images: uint8 [h,w,3] arrays (host) or CUDA tensors, all mapping to the SAME resized size (group them with
-    ``get_multi_scale_size`` first).  Returns (x [B,3,H,W] float32 on ``device``, centers, scales)."""
+    ``group_by_resized_size`` first).  Returns (x [B,3,H,W] float32 on ``device``, centers, scales) and, with
+    ``return_inverse``, also the float64 [B,6] inverse matrices the decoder back-projects with."""
     device = torch.device(device)
-    geo = [get_multi_scale_size(im, input_size, current_scale, min_scale) for im in images]
-    size = geo[0][0]
-    if any(g[0] != size for g in geo):
-        raise _lib.HpdError("prepare_input: images of one call must share the resized size; got %s" % sorted({g[0] for g in geo}))
-    dev_imgs, mats = [], []
-    for im, (_, center, scale) in zip(images, geo):
+    sizes, centers, scales, fwd, inv = prepare_geometry([im.shape[:2] for im in images], input_size, current_scale, min_scale)
+    if (sizes != sizes[0]).any():
+        raise _lib.HpdError("prepare_input: images of one call must share the resized size; got %s"
+                            % sorted({(int(w), int(h)) for w, h in sizes}))
+    dev_imgs = []
+    for im in images:
         t = im if isinstance(im, torch.Tensor) else torch.from_numpy(np.ascontiguousarray(im))
         if t.dtype != torch.uint8 or t.dim() != 3 or t.shape[2] != 3:
             raise _lib.HpdError("prepare_input: images must be uint8 [h,w,3]")
         dev_imgs.append(t.to(device, non_blocking=True).contiguous())
-        mats.append(get_affine_transform(center, scale, 0, size).ravel())
-    x = torch.ops.hpd.prepare_input(dev_imgs, torch.from_numpy(np.stack(mats)), size[1], size[0], list(mean), list(std))
-    return x, [g[1] for g in geo], [g[2] for g in geo]
+    x = torch.ops.hpd.prepare_input(dev_imgs, torch.from_numpy(fwd), int(sizes[0, 1]), int(sizes[0, 0]), list(mean), list(std))
+    out = (x, [(int(c[0]), int(c[1])) for c in centers], [(float(s[0]), float(s[1])) for s in scales])
+    return out + (inv,) if return_inverse else out
 
 
 def group_by_resized_size(shapes_hw: Sequence[Tuple[int, int]], input_size: int, current_scale: float = 1,
                           min_scale: float = 1) -> dict:
     """{(w_resized, h_resized): [indices]} -- images that can share one batched network call."""
     groups: dict = {}
-    for i, hw in enumerate(shapes_hw):
-        groups.setdefault(get_multi_scale_size(hw, input_size, current_scale, min_scale)[0], []).append(i)
+    sizes = prepare_geometry(list(shapes_hw), input_size, current_scale, min_scale)[0]
+    for i, (w, h) in enumerate(sizes):
+        groups.setdefault((int(w), int(h)), []).append(i)
     return groups

@@ -107,11 +107,10 @@ class InferenceKeypointsModel:
         groups = geometry.group_by_resized_size([im.shape[:2] for im in raw_images], self.input_size, 1.0, min_scale)
         for size, idxs in groups.items():
             imgs = [raw_images[i] for i in idxs]
-            x, centers, scales = geometry.prepare_input(imgs, self.input_size, self.device, 1.0, min_scale)
+            x, centers, scales, minv = geometry.prepare_input(imgs, self.input_size, self.device, 1.0, min_scale,
+                                                              return_inverse=True)
             extra = [geometry.prepare_input(imgs, self.input_size, self.device, s, min_scale)[0]
                      for s in self.test_scales if s != 1.0]
-            minv = np.stack([geometry.get_affine_transform(c, s, 0, size, inverse=True).ravel()
-                             for c, s in zip(centers, scales)])
             res = self.forward_decode(x, inv_affine=minv, extra_scales=extra)
             rec = res.host()
             for j, i in enumerate(idxs):

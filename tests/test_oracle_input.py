@@ -76,6 +76,22 @@ def test_library_host_geometry_many_sizes_against_oracle():
                                   input_oracle.get_affine_transform(want[1], want[2], want[0], bool(inverse)))
 
 
+def test_batched_geometry_entry_point_equals_the_single_image_ones():
+    """hpd_prepare_geometry (one call for n images) == hpd_multi_scale_size + hpd_get_affine_transform per image."""
+    from hpdecode import geometry
+    rng = np.random.default_rng(11)
+    shapes = [(int(h), int(w)) for h, w in rng.integers(40, 1500, (50, 2))]
+    for cur, mn in ((1, 1), (1.5, 0.5)):
+        sizes, centers, scales, fwd, inv = geometry.prepare_geometry(shapes, 512, cur, mn)
+        for i, hw in enumerate(shapes):
+            size, center, scale = geometry.get_multi_scale_size(hw, 512, cur, mn)
+            assert tuple(sizes[i]) == size and tuple(centers[i]) == center and tuple(scales[i]) == scale
+            assert np.array_equal(fwd[i].reshape(2, 3), geometry.get_affine_transform(center, scale, 0, size))
+            assert np.array_equal(inv[i].reshape(2, 3), geometry.get_affine_transform(center, scale, 0, size, inverse=True))
+    groups = geometry.group_by_resized_size([(480, 640), (640, 480), (479, 640)], 512)
+    assert groups == {(704, 512): [0, 2], (512, 704): [1]}
+
+
 @needs_reference
 def test_input_oracle_against_live_reference_cv2_and_torchvision():
     sys.path.insert(0, REF)
