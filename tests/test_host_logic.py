@@ -108,6 +108,38 @@ def _worker_equal(rank, world, port, q):
     dist.destroy_process_group()
 
 
+def _worker_rows(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from hpdecode.parallel import gather_rows
+    block = (torch.arange(40, dtype=torch.int32) % 251 + 7 * rank).to(torch.uint8)     # one rank's records, flattened
+    out = torch.zeros((world, 40), dtype=torch.uint8) if rank == 0 else None
+    got = gather_rows(block, out, dst=0)
+    if rank == 0:
+        assert got is out
+        q.put(out.numpy())
+    else:
+        assert got is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+def test_gather_rows_world2_gloo():
+    """bench.py's gather of the result records: rank r's flat uint8 block lands in row r on rank 0."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 33500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker_rows, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=120)
+    for p in procs:
+        p.join(timeout=120)
+        assert p.exitcode == 0
+    base = (np.arange(40) % 251).astype(np.uint8)
+    assert np.array_equal(got, np.stack([base, base + 7]))
+
+
 def test_gather_packed_equal_world2_gloo():
     """The equal-shard gather bench.py uses at N > 1: rank r's rows land at [r*b, (r+1)*b) of the preallocated tensor."""
     ctx = mp.get_context("spawn")
