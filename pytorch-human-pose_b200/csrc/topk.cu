@@ -194,6 +194,9 @@ struct WarpHeap {
   // bit order: __push_heap stops at the deepest path node whose element is not greater than the value (highest
   // such bit), every path node above it takes its path child's element (one shuffle), that node takes the value.
   // Same comparisons, same outcome as adjust(0, len, ...); ~3 ballots + 2 shuffles deep instead of a 6-level chain.
+  // GUARDED: the sift happens only if comp(value, first[0]), i.e. value > top -- __heap_select's test -- decided
+  // inside by a ballot that is issued together with the others instead of ahead of them (no branch on the way).
+  template <bool GUARDED = false>
   __device__ __forceinline__ void adjust_root(int len, float val, int idx) {
     const int sib = (lane & 1) ? lane + 1 : lane - 1;
     const float sv = __shfl_sync(kFull, v, sib & 31);
@@ -206,14 +209,15 @@ struct WarpHeap {
     const bool on_path = lane >= 1 && (sel & anc) == anc;
     const unsigned path = __ballot_sync(kFull, on_path);               // nodes of the path below the root
     const unsigned above = __ballot_sync(kFull, comp_gt(v, val));      // bit n: comp(first[n], value)
+    const bool enter = !GUARDED || (__ballot_sync(kFull, lane == 0 && comp_gt(val, v)) != 0u);
     const unsigned stop = path & ~above;
     const int t = stop ? 31 - __clz(stop) : 0;                         // where the value lands
     int src = lane;
-    if ((lane == 0 || on_path) && lane < t) src = ((path >> (2 * lane + 1)) & 1u) ? 2 * lane + 1 : 2 * lane + 2;
+    if (enter && (lane == 0 || on_path) && lane < t) src = ((path >> (2 * lane + 1)) & 1u) ? 2 * lane + 1 : 2 * lane + 2;
     const float nv = __shfl_sync(kFull, v, src);
     const int ni = __shfl_sync(kFull, i, src);
     v = nv; i = ni;
-    if (lane == t) { v = val; i = idx; }
+    if (enter && lane == t) { v = val; i = idx; }
   }
   __device__ __forceinline__ void make(int len) {
     if (len < 2) return;
@@ -914,8 +918,9 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_split_kernel(const f
 //      distinct pixels, so this is a lower bound of the heap top at the segment's start -- seeds a sorted sink with M
 //      placeholders at that value and logs every element of its segment that enters the sink: a superset of what
 //      enters the heap there, in index order;
-//   3. warp 0 replays the concatenated logs through the libstdc++ heap (slot i in lane i), filtering against the
-//      live top, and sorts.
+//   3. warp 0 owns the libstdc++ heap (slot i in lane i): it streams its own segment -- the first pixels of the row --
+//      straight through it, then replays the logs of the other segments in order, each as soon as it is complete,
+//      filtering against the live top, and sorts.
 constexpr int kTiedLogCap = 512;
 // segment s covers [kSegFrac[s], kSegFrac[s+1]) / 1024 of the row's words (rounded up to multiples of 8 words): with
 // ~M/i entries per element every segment logs a few dozen, the first one (which warp 0 both logs and replays) the fewest
@@ -964,35 +969,41 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_tied_rows_kernel(con
   } else {
     TP_MARK(1);
   }
-  SortedSink seg;
-  seg.M = M; seg.lane = lane;
-  seg.log_v = s_logv[warp]; seg.log_i = s_logi[warp]; seg.log_cap = kTiedLogCap;
-  if (floor_s > -INFINITY) seg.init_floor(floor_s);
-  else seg.init_empty();
-  TP_MARK(2);
-  scan_range(seg, hm, mk, wm, W, wpr, w_begin, w_end, 0, lane);
-  TP_MARK(3);
+  if (warp != 0) {
+    SortedSink seg;
+    seg.M = M; seg.lane = lane;
+    seg.log_v = s_logv[warp]; seg.log_i = s_logi[warp]; seg.log_cap = kTiedLogCap;
+    if (floor_s > -INFINITY) seg.init_floor(floor_s);
+    else seg.init_empty();
+    TP_MARK(2);
+    scan_range(seg, hm, mk, wm, W, wpr, w_begin, w_end, 0, lane);
+    TP_MARK(3);
 #ifdef HPD_TOPK_PROFILE
-  if (lane == 0) { s_tp[warp][0] = tp[1] - tp[0]; s_tp[warp][1] = tp[2] - tp[1]; s_tp[warp][2] = tp[3] - tp[2]; }
+    if (lane == 0) { s_tp[warp][0] = tp[1] - tp[0]; s_tp[warp][1] = tp[2] - tp[1]; s_tp[warp][2] = tp[3] - tp[2]; }
 #endif
-  __syncwarp();
-  if (lane == 0) {
-    s_nlog[warp] = seg.n_log;
-    __threadfence_block();
-    *(volatile int*)&s_ready[warp] = 1;
+    __syncwarp();
+    if (lane == 0) {
+      s_nlog[warp] = seg.n_log;
+      __threadfence_block();
+      *(volatile int*)&s_ready[warp] = 1;
+    }
+    return;
   }
-  if (warp != 0) return;
-  TP_MARK(4);
+  TP_MARK(2);
 
-  // Warp 0 replays segment after segment, each as soon as its warp has finished logging it (the later segments
-  // are still being streamed while the early ones, which hold most of the entries, go through the heap).
+  // Warp 0 owns the heap.  Its own segment -- the first pixels of the row, where most of the entries are -- goes
+  // through the exact heap directly (no log in between); then it replays segment after segment, each as soon as its
+  // warp has finished logging it (the later segments are still being streamed meanwhile).
   float out_v = 0.f;
   int out_i = 0;
   bool logs_ok = true;
   WarpHeapSink exact;
   exact.M = M; exact.lane = lane;
   exact.init(first_element(hm, mk, W, wpr, M, lane));
-  for (int w = 0; w < kSplitWarps && logs_ok; ++w) {
+  scan_range(exact, hm, mk, wm, W, wpr, w_begin, w_end, M, lane);
+  TP_MARK(3);
+  TP_MARK(4);
+  for (int w = 1; w < kSplitWarps && logs_ok; ++w) {
     while (*(volatile int*)&s_ready[w] == 0) {}
     __threadfence_block();
     const int n = *(volatile int*)&s_nlog[w];
@@ -1014,8 +1025,8 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_tied_rows_kernel(con
         j = pass ? __ffs(pass) - 1 : j;
         cvj = s_logv[w][i0 + j];
         cij = s_logi[w][i0 + j];
-        // comp(*i, *first): the element enters iff it is greater than the heap's top right now
-        if (__ballot_sync(kFull, lane == 0 && cur_v > exact.h.v)) exact.h.adjust_root(M, cur_v, cur_i);
+        // comp(*i, *first): the element enters iff it is greater than the heap's top right now (tested inside)
+        exact.h.adjust_root<true>(M, cur_v, cur_i);
       }
     }
   }
@@ -1026,7 +1037,7 @@ __global__ void __launch_bounds__(kSplitWarps * 32, 1) topk_tied_rows_kernel(con
 #ifdef HPD_TOPK_PROFILE
     if (lane == 0 && atomicAdd(&tp_printed, 1) < 80) {
       int tot = 0;
-      for (int w = 0; w < kSplitWarps; ++w) tot += s_nlog[w];
+      for (int w = 1; w < kSplitWarps; ++w) tot += s_nlog[w];
       printf("tied row %d: own segment %lld, replay+wait %lld, sort %lld, total %lld cycles; %d log entries\n", row, tp[3] - tp[0],
              tp[5] - tp[4], tp[6] - tp[5], tp[6] - tp[0], tot);
     }
