@@ -64,6 +64,7 @@ class DecodeResult:
 
     def __init__(self, bufs: ops.DecodeBuffers):
         self.bufs = bufs
+        self._generation = getattr(bufs, "generation", 0)   # a later decode into the same buffer set bumps it
         self.agg_hm = bufs.agg_hm          # [B,K,H,W]
         self.agg_tags = bufs.agg_tags      # [B,K,H,W,E]
         self.poses = bufs.poses            # [B,M,K,3+E]
@@ -72,12 +73,20 @@ class DecodeResult:
         self.flags = bufs.flags
         self.records = bufs.records        # [B,row_bytes] uint8, written by the last kernel's epilogue
 
+    def _check_live(self):
+        if getattr(self.bufs, "generation", 0) != self._generation:
+            raise ops._lib.HpdError("this DecodeResult was overwritten by a later decode into the same buffer set "
+                                    "(same shape and slot): read or clone() a result before decoding again, or use "
+                                    "distinct slots")
+
     def packed(self) -> torch.Tensor:
         """The device tensor that holds everything a caller reads after a decode (one row per image):
         no ATen op runs here, the kernels wrote this layout themselves."""
+        self._check_live()
         return self.records
 
     def host(self) -> "Records":
+        self._check_live()
         B, M, K, D = self.poses.shape
         return Records(self.records.cpu().numpy(), M, K, D - 3)
 
@@ -154,6 +163,7 @@ class BottomUpDecoder:
         self._set_inv_affine(bufs, inv_affine)     # float64 [B,6]: back-projection of the records' COCO section
         params = ops.make_params(B, self.num_kpts, H, W, E, self.max_num_people, self.det_thr, self.tag_thr,
                                  self.adjust, self.refine, len(scales), tag_scale, tags_preflipped=tags_preflipped)
+        bufs.generation = getattr(bufs, "generation", 0) + 1
         ops.run_decode(scales, bufs, params)
         return DecodeResult(bufs)
 
@@ -234,6 +244,7 @@ class DecodePipeline:
             for t in s.values():
                 if t is not None and t.is_cuda:
                     t.record_stream(st)
+        bufs.generation = getattr(bufs, "generation", 0) + 1
         res = DecodeResult(bufs)
         with torch.cuda.stream(st):
             if ln["used"]:

@@ -196,3 +196,21 @@ def test_extreme_max_people(M, oracle):
         assert out[b][0].shape == ref["grouped_joints"].shape
         assert np.array_equal(_bits(out[b][0]), _bits(ref["grouped_joints"]))
         assert np.array_equal(_bits(out[b][1]), _bits(ref["person_scores"]))
+
+
+def test_stale_result_is_refused():
+    """a DecodeResult views the decoder's cached buffer set; reading it after a later decode of the same
+    shape and slot raises instead of silently returning the newer batch."""
+    from hpdecode import BottomUpDecoder
+    from hpdecode._lib import HpdError
+    dec = BottomUpDecoder(17, 30, 0.05, 0.5, "cuda:0")
+    a = _dev(synth.crowd(1, 192, persons=4, flip=True, seed=1))
+    b = _dev(synth.crowd(1, 192, persons=7, flip=True, seed=2))
+    first = dec.decode(a, (192, 192))
+    kept = first.to_numpy()
+    second = dec.decode(b, (192, 192))
+    with pytest.raises(HpdError):
+        first.to_numpy()
+    assert len(second.to_numpy()[0][0]) != 0 and len(kept[0][0]) != 0
+    other = dec.decode(a, (192, 192), slot=1)          # distinct slots can be held together
+    assert len(second.to_numpy()) == 1 and len(other.to_numpy()) == 1
