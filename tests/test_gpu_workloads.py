@@ -161,3 +161,30 @@ def test_pipeline_with_cuda_graphs_and_records_ring(oracle):
         ref = oracle.parse(hm_o, tg_o, 30, 0.05, 0.5)
         gj, ps = rec.image(b)
         assert np.array_equal(_bits(gj), _bits(ref["grouped_joints"])) and np.array_equal(_bits(ps), _bits(ref["person_scores"]))
+
+
+def test_pipeline_passes_the_back_projection_matrices():
+    """DecodePipeline.submit(inv_affine=...) writes the same records (COCO section back-projected per image) as
+    BottomUpDecoder.decode(inv_affine=...), eagerly and under CUDA graphs (the matrices are then baked-in pointers,
+    so the same device tensor must be passed again)."""
+    from hpdecode import BottomUpDecoder, geometry, synth
+    from hpdecode.decoder import DecodePipeline
+    dec = BottomUpDecoder(17, 30, 0.05, 0.5, "cuda:0")
+    host = synth.crowd(2, 256, persons=6, flip=True, seed=41)
+    dev = [{k: torch.from_numpy(v).cuda() for k, v in s.items()} for s in host]
+    minv = np.stack([geometry.get_affine_transform((320, 240), (640.0, 480.0), 0, (256, 256), inverse=True).ravel(),
+                     geometry.get_affine_transform((100, 90), (250.0, 250.0), 0, (256, 256), inverse=True).ravel()])
+    want = dec.decode(dev, (256, 256), slot=5, inv_affine=minv).records.clone()
+    plain = dec.decode(dev, (256, 256), slot=6).records.clone()
+    assert not torch.equal(want, plain)                                  # the projection really changed the records
+    pipe = DecodePipeline(dec, depth=2)
+    got = [pipe.submit(dev, (256, 256), inv_affine=minv) for _ in range(3)]
+    pipe.drain()
+    torch.cuda.synchronize()
+    assert torch.equal(got[-1].records, want) and torch.equal(got[-2].records, want)
+    minv_dev = torch.from_numpy(minv).cuda()
+    gpipe = DecodePipeline(dec, depth=2, use_graphs=True)
+    out = [gpipe.submit(dev, (256, 256), inv_affine=minv_dev) for _ in range(4)]
+    gpipe.drain()
+    torch.cuda.synchronize()
+    assert torch.equal(out[-1].records, want) and torch.equal(out[-2].records, want)
